@@ -1,0 +1,88 @@
+// Shared helpers for the HandMvNet B200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace hmv {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: no exception ever crosses the C boundary -------------------------------
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define HMV_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            hmv::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                           __FILE__ + ":" + std::to_string(__LINE__));                         \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define HMV_CHECK(cond, msg)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            hmv::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +             \
+                           std::to_string(__LINE__));                                          \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// ---- scalar conversion helpers used by the templated (bf16 | fp32) kernels -------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+    return __bfloat1622float2(h);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Epilogue description shared by the tensor-core and the fp32 implicit-GEMM kernels.
+enum OutMode { OUT_BF16_ROWMAJOR = 0, OUT_F32_ROWMAJOR = 1, OUT_F32_NCHW = 2 };
+enum ResMode { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
+enum ActMode { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct Epilogue {
+    void* out;              // [M, ldc] (row-major modes) or [M/hw, N, hw] (NCHW mode)
+    const float* bias;      // [N_alloc] fp32 (never null; zero padded)
+    const void* residual;   // [*, res_ld] or null
+    int ldc;
+    int out_mode;
+    int res_mode;
+    int res_ld;
+    int res_group;          // residual row = (m / res_group) * res_stride + m % res_group
+    int res_stride;
+    int act;
+    int M;                  // valid rows
+    int N;                  // valid cols (only enforced in NCHW mode; row-major pitches cover N_alloc)
+    int hw;                 // pixels per image (NCHW mode)
+};
+
+}  // namespace hmv

@@ -1,0 +1,439 @@
+// See conv_gemm_tc.cuh for the design.  sm_100a only: tcgen05.mma / tcgen05.ld / TMEM alloc,
+// cp.async.bulk.tensor (TMA) and mbarrier pipelines are written as inline PTX.
+#include "conv_gemm_tc.cuh"
+
+namespace hmv {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug must not hang the GPU.  ~2 s at 2 GHz, then flag + bail out.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (true) {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (clock64() - t0 > 4000000000LL) {
+            atomicExch(err_flag, code);
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, 128B-swizzled operand descriptor (matches what TMA SWIZZLE_128B wrote):
+// 8-row x 128-byte atoms, SBO = 1024 B between atoms, descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;             // LBO: unused for swizzled K-major
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO
+    d |= static_cast<uint64_t>(1) << 46;             // version
+    d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+    return d;
+}
+// D(f32) += A(bf16, K-major) * B(bf16, K-major)^T ; M = 128, N = bn
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+           (static_cast<uint32_t>(kTcBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: 16 consecutive output columns of one row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_16(const Epilogue& ep, float (&v)[16], int row, int col0) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+    if (ep.res_mode != RES_NONE) {
+        const size_t rrow = static_cast<size_t>(row / ep.res_group) * ep.res_stride + row % ep.res_group;
+        if (ep.res_mode == RES_BF16) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.residual) + rrow * ep.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint4 q = __ldg(rp + i);
+                const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+                v[8 * i + 0] += a.x; v[8 * i + 1] += a.y; v[8 * i + 2] += b.x; v[8 * i + 3] += b.y;
+                v[8 * i + 4] += c.x; v[8 * i + 5] += c.y; v[8 * i + 6] += d.x; v[8 * i + 7] += d.y;
+            }
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(ep.residual) + rrow * ep.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 q = __ldg(rp + i);
+                v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+        }
+    }
+    if (ep.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (ep.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (ep.out_mode == OUT_BF16_ROWMAJOR) {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + static_cast<size_t>(row) * ep.ldc + col0);
+        uint4 q0, q1;
+        q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+        q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+        q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+        q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+        op[0] = q0;
+        op[1] = q1;
+    } else if (ep.out_mode == OUT_F32_ROWMAJOR) {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldc + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {  // OUT_F32_NCHW: lanes are consecutive pixels -> coalesced per channel
+        const int img = row / ep.hw, pix = row % ep.hw;
+        float* op = static_cast<float*>(ep.out) + (static_cast<size_t>(img) * ep.N) * ep.hw + pix;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (col0 + i < ep.N) op[static_cast<size_t>(col0 + i) * ep.hw] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg {
+    static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;       // 16 KiB
+    static constexpr int kBBytes = BN * kTcBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                     : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+    static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * Cfg::kStages;
+    const uint32_t tfull0 = empty0 + 8 * Cfg::kStages;
+    const uint32_t tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = p.num_taps * p.cblks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool alive = true;
+            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int m_tile = tile / p.num_n_tiles;
+                const int w0 = p.flat ? m_tile * kTcBlockM : 0;
+                const int h0 = p.flat ? 0 : (m_tile % p.tpi) * p.hbox;
+                const int img = p.flat ? 0 : m_tile / p.tpi;
+                int kb = 0;
+                for (int t = 0; t < p.num_taps && alive; ++t) {
+                    const TcTap tap = p.taps[t];
+                    for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
+                        if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 1)) { alive = false; break; }
+                        const uint32_t fb = full0 + 8 * stage;
+                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                        mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                        tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
+                        tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            bool alive = true;
+            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+                if (!mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, p.err_flag, 2)) { alive = false; break; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 3)) { alive = false; break; }
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+                        const uint64_t adesc = make_sw128_desc(sa + k * kTcUmmaK * 2);
+                        const uint64_t bdesc = make_sw128_desc(sb + k * kTcUmmaK * 2);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                if (!alive) break;
+                umma_commit(tfull0 + 8 * acc);           // accumulator ready for the epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        bool alive = true;
+        for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+            const int n_tile = tile % p.num_n_tiles;
+            const int m_tile = tile / p.num_n_tiles;
+            if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) { alive = false; break; }
+            tc_fence_after();
+            const int row = m_tile * kTcBlockM + quarter * 32 + lane;
+            const bool row_ok = row < p.ep.M;
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(t0 + c, r0);
+                if (c + 16 < BN) tmem_ld16(t0 + c + 16, r1);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
+                if (c + 16 < BN) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+template <int BN>
+static int set_attr() {
+    HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<BN>::kSmemBytes));
+    return 0;
+}
+
+int tc_init() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    HMV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    HMV_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    if (set_attr<32>() || set_attr<64>() || set_attr<128>() || set_attr<176>() || set_attr<256>()) return 1;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+static int encode(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box) {
+    HMV_CHECK(g_encode != nullptr, "tc_init() was not called");
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) s[i] = strides[i];
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, e,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        std::string m = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ") rank " +
+                        std::to_string(rank) + " dims";
+        for (int i = 0; i < rank; ++i) m += " " + std::to_string(dims[i]);
+        m += " strides";
+        for (int i = 0; i < rank - 1; ++i) m += " " + std::to_string(strides[i]);
+        m += " box";
+        for (int i = 0; i < rank; ++i) m += " " + std::to_string(box[i]);
+        set_error(m);
+        return 1;
+    }
+    return 0;
+}
+
+int tc_make_tmap_act(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                     const uint32_t box[5]) {
+    return encode(out, base, 5, dims, strides_bytes, box);
+}
+
+int tc_make_tmap_wgt(CUtensorMap* out, const void* base, uint64_t k_total, uint64_t n_alloc, int bn) {
+    const uint64_t dims[2] = {k_total, n_alloc};
+    const uint64_t strides[1] = {k_total * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kTcBlockK), static_cast<uint32_t>(bn)};
+    return encode(out, base, 2, dims, strides, box);
+}
+
+int tc_pick_bn(int n) {
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    if (n <= 128) return 128;
+    if (n % 256 == 0) return 256;
+    if (n % 176 == 0) return 176;   // 528 = 3 x 176 (d_model 524 padded)
+    if (n % 128 == 0) return 128;
+    return 0;
+}
+
+template <int BN>
+static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
+    const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    conv_gemm_tc_kernel<BN><<<grid, kTcThreads, TcCfg<BN>::kSmemBytes, stream>>>(l.tmA, l.tmB, l.p);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream) {
+    if (l.p.num_m_tiles <= 0 || l.p.num_n_tiles <= 0) return 0;
+    switch (l.bn) {
+        case 32: return launch_bn<32>(l, num_sms, stream);
+        case 64: return launch_bn<64>(l, num_sms, stream);
+        case 128: return launch_bn<128>(l, num_sms, stream);
+        case 176: return launch_bn<176>(l, num_sms, stream);
+        case 256: return launch_bn<256>(l, num_sms, stream);
+    }
+    set_error("tc_launch: unsupported BN " + std::to_string(l.bn));
+    return 1;
+}
+
+}  // namespace hmv

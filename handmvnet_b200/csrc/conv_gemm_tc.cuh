@@ -1,0 +1,56 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// One persistent, warp-specialised kernel covers every GEMM-shaped op of the path
+// (reference call sites: backbones/resnet.py:124-144 Bottleneck convs, :218 stem,
+// layers.py:318-334 pose_net / SampleNet convs, layers.py:213-215,224,165-170 the fusion
+// linears):   D[m, n] = act( sum_taps sum_c A_tap[m, c] * W[n, tap, c] + bias[n] (+ res[m, n]) )
+//
+//   * A (activations, NHWC bf16) is described by ONE 5-D TMA tensor map
+//     (C, W', A, H', N); a "tap" is a coordinate offset (c_off, dw, a, dh) into that map, so
+//     3x3/pad-1 convs are 9 shifted box loads with hardware zero fill, stride-2 convs address
+//     the input through its (row-parity, col-parity) view, the 7x7/2 stem uses an overlapping
+//     16-byte pixel-pair stride, and 1x1 convs / linears are the single-tap "flat" case.
+//   * W is [N_alloc, K] K-major bf16 (BN scale folded in), one 2-D tensor map.
+//   * Both land in 128B-swizzled shared memory (4..8 stage mbarrier ring) and feed
+//     tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread; the fp32
+//     accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
+//     tile i+1.  Epilogue warps read TMEM with tcgen05.ld (32 lanes x 32b), add the folded-BN
+//     bias, the optional residual, apply ReLU/GELU and store bf16 NHWC / fp32 / fp32-NCHW.
+#pragma once
+#include "common.cuh"
+
+namespace hmv {
+
+constexpr int kTcBlockM = 128;
+constexpr int kTcBlockK = 64;          // bf16 elements -> 128 B = one swizzle-128B row
+constexpr int kTcUmmaK = 16;
+constexpr int kTcThreads = 192;        // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kTcMaxTaps = 9;
+
+struct TcTap { int c_off, dw, a, dh; };
+
+struct TcParams {
+    int num_m_tiles, num_n_tiles;
+    int num_taps, cblks;               // K blocks per tile = num_taps * cblks
+    int flat;                          // 1: A is [M, K] (coord1 = m_tile*128); 0: spatial tile
+    int tpi, hbox;                     // spatial: tiles per image, rows of H' per tile
+    TcTap taps[kTcMaxTaps];
+    Epilogue ep;
+    int* err_flag;                     // set to non-zero on an mbarrier timeout
+};
+
+struct TcLaunch {                      // everything needed to enqueue one layer
+    CUtensorMap tmA, tmB;
+    TcParams p;
+    int bn;
+};
+
+// Host API -------------------------------------------------------------------------------------
+int tc_init();                                               // resolves cuTensorMapEncodeTiled, sets smem attrs
+int tc_make_tmap_act(CUtensorMap* out, const void* base, const uint64_t dims[5],
+                     const uint64_t strides_bytes[4], const uint32_t box[5]);
+int tc_make_tmap_wgt(CUtensorMap* out, const void* base, uint64_t k_total, uint64_t n_alloc, int bn);
+int tc_pick_bn(int n);                                       // tile width for a given output width
+int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream);
+
+}  // namespace hmv

@@ -1,0 +1,549 @@
+// Memory-/latency-bound kernels around the GEMMs: input packing, max-pool, soft-argmax,
+// bilinear neighbour gather, token assembly (+ positional encodings), attention core,
+// LayerNorm and the Chebyshev graph-conv head.  Templated on the activation type
+// (bf16 on the tensor-core path, float in fp32 check mode).
+#include "kernels.cuh"
+
+namespace hmv {
+
+// ------------------------------------------------------------------------------------------------
+// input packing: fp32 NCHW -> padded NHWC4
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int H, int W, int Hp, int Wp,
+                                  int pad, size_t total) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int wp = static_cast<int>(idx % Wp);
+    const int hp = static_cast<int>((idx / Wp) % Hp);
+    const size_t n = idx / (static_cast<size_t>(Wp) * Hp);
+    const int h = hp - pad, w = wp - pad;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+        const float* px = x + (n * 3 * H + h) * W + w;
+        v0 = __ldg(px);
+        v1 = __ldg(px + static_cast<size_t>(H) * W);
+        v2 = __ldg(px + 2 * static_cast<size_t>(H) * W);
+    }
+    if constexpr (sizeof(T) == 2) {
+        uint2 q;
+        q.x = pack_bf16x2(v0, v1);
+        q.y = pack_bf16x2(v2, 0.f);
+        reinterpret_cast<uint2*>(out)[idx] = q;
+    } else {
+        reinterpret_cast<float4*>(out)[idx] = make_float4(v0, v1, v2, 0.f);
+    }
+}
+
+template <typename T>
+int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, int Wp, int pad, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(n_img) * Hp * Wp;
+    if (total == 0) return 0;
+    pack_input_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, out, H, W, Hp, Wp, pad, total);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int pack_input_launch<bf16>(const float*, bf16*, int, int, int, int, int, int, cudaStream_t);
+template int pack_input_launch<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 / 2 / pad 1, NHWC, 16-byte vectors along C
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, int Win, int Hout, int Wout,
+                               int C, size_t total) {
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = C / VEC;
+    const int c = static_cast<int>(idx % cv) * VEC;
+    const int ow = static_cast<int>((idx / cv) % Wout);
+    const int oh = static_cast<int>((idx / (static_cast<size_t>(cv) * Wout)) % Hout);
+    const size_t n = idx / (static_cast<size_t>(cv) * Wout * Hout);
+    float m[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int ih = oh * 2 - 1 + r;
+        if (ih < 0 || ih >= Hin) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int iw = ow * 2 - 1 + s;
+            if (iw < 0 || iw >= Win) continue;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((n * Hin + ih) * Win + iw) * C + c));
+            if constexpr (sizeof(T) == 2) {
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16x2(w4[i]);
+                    m[2 * i] = fmaxf(m[2 * i], f.x);
+                    m[2 * i + 1] = fmaxf(m[2 * i + 1], f.y);
+                }
+            } else {
+                m[0] = fmaxf(m[0], __uint_as_float(q.x)); m[1] = fmaxf(m[1], __uint_as_float(q.y));
+                m[2] = fmaxf(m[2], __uint_as_float(q.z)); m[3] = fmaxf(m[3], __uint_as_float(q.w));
+            }
+        }
+    }
+    uint4 o;
+    if constexpr (sizeof(T) == 2) {
+        o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]);
+        o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    } else {
+        o.x = __float_as_uint(m[0]); o.y = __float_as_uint(m[1]); o.z = __float_as_uint(m[2]); o.w = __float_as_uint(m[3]);
+    }
+    *reinterpret_cast<uint4*>(out + ((n * Hout + oh) * Wout + ow) * C + c) = o;
+}
+
+template <typename T>
+int maxpool_launch(const T* in, T* out, int n_img, int Hin, int Win, int C, cudaStream_t s) {
+    constexpr int VEC = 16 / sizeof(T);
+    HMV_CHECK(C % VEC == 0, "maxpool: C must be a multiple of the 16-byte vector");
+    const int Hout = (Hin + 2 - 3) / 2 + 1, Wout = (Win + 2 - 3) / 2 + 1;
+    const size_t total = static_cast<size_t>(n_img) * Hout * Wout * (C / VEC);
+    if (total == 0) return 0;
+    maxpool_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, Hin, Win, Hout, Wout, C, total);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int maxpool_launch<bf16>(const bf16*, bf16*, int, int, int, int, cudaStream_t);
+template int maxpool_launch<float>(const float*, float*, int, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// soft-argmax: one warp per heatmap, fp32 throughout
+// ------------------------------------------------------------------------------------------------
+__global__ void softargmax_kernel(const float* __restrict__ hm, float* __restrict__ xy, float* __restrict__ xy_scaled,
+                                  int n_maps, int H, int W, float temperature, float scale) {
+    const int map = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (map >= n_maps) return;
+    const int hw = H * W;
+    const float4* p = reinterpret_cast<const float4*>(hm + static_cast<size_t>(map) * hw);
+    const int nvec = hw >> 2;
+    float mx = -INFINITY;
+    for (int i = lane; i < nvec; i += 32) {
+        const float4 q = __ldg(p + i);
+        mx = fmaxf(mx, fmaxf(fmaxf(q.x * temperature, q.y * temperature), fmaxf(q.z * temperature, q.w * temperature)));
+    }
+    mx = warp_max(mx);
+    float se = 0.f, sx = 0.f, sy = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+        const float4 q = __ldg(p + i);
+        const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = i * 4 + k;
+            const float e = expf(v[k] * temperature - mx);
+            se += e;
+            sx += e * static_cast<float>(idx % W);
+            sy += e * static_cast<float>(idx / W);
+        }
+    }
+    se = warp_sum(se); sx = warp_sum(sx); sy = warp_sum(sy);
+    if (lane == 0) {
+        const float x = sx / se, y = sy / se;
+        xy[2 * map] = x; xy[2 * map + 1] = y;
+        if (xy_scaled) { xy_scaled[2 * map] = x * scale; xy_scaled[2 * map + 1] = y * scale; }
+    }
+}
+
+int softargmax_launch(const float* hm, float* xy, float* xy_scaled, int n_maps, int H, int W, float temperature,
+                      float scale, cudaStream_t s) {
+    if (n_maps == 0) return 0;
+    HMV_CHECK((H * W) % 4 == 0, "softargmax: H*W must be a multiple of 4");
+    softargmax_kernel<<<(n_maps + 7) / 8, 256, 0, s>>>(hm, xy, xy_scaled, n_maps, H, W, temperature, scale);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear neighbour gather (grid_sample align_corners=True, zeros padding)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sample_gather_kernel(const T* __restrict__ feat, const float* __restrict__ xy, T* __restrict__ rows,
+                                     float* __restrict__ wts, int H, int W, int C) {
+    const int nj = blockIdx.x;                 // n * 21 + j
+    const int n = nj / kJoints;
+    const float x = xy[2 * nj], y = xy[2 * nj + 1];
+    // same op order as the reference: nets.py:48-49 then grid_sampler unnormalize (align_corners)
+    const float gx = x / static_cast<float>(W - 1) * 2.f - 1.f;
+    const float gy = y / static_cast<float>(H - 1) * 2.f - 1.f;
+    const float ix = ((gx + 1.f) / 2.f) * static_cast<float>(W - 1);
+    const float iy = ((gy + 1.f) / 2.f) * static_cast<float>(H - 1);
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float wq[4] = {(x0 + 1.f - ix) * (y0 + 1.f - iy), (ix - x0) * (y0 + 1.f - iy),
+                         (x0 + 1.f - ix) * (iy - y0), (ix - x0) * (iy - y0)};
+    const int vec_per_row = C * static_cast<int>(sizeof(T)) / 16;
+    for (int q = 0; q < 4; ++q) {
+        const int xi = static_cast<int>(x0) + (q & 1), yi = static_cast<int>(y0) + (q >> 1);
+        const bool ok = xi >= 0 && xi < W && yi >= 0 && yi < H;     // also false for NaN coords
+        uint4* dst = reinterpret_cast<uint4*>(rows + (static_cast<size_t>(nj) * 4 + q) * C);
+        if (ok) {
+            const uint4* src = reinterpret_cast<const uint4*>(feat + ((static_cast<size_t>(n) * H + yi) * W + xi) * C);
+            for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) dst[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (threadIdx.x == 0) wts[nj * 4 + q] = ok ? wq[q] : 0.f;
+    }
+}
+
+template <typename T>
+int sample_gather_launch(const T* feat, const float* xy, T* rows, float* wts, int n_img, int H, int W, int C,
+                         cudaStream_t s) {
+    if (n_img == 0) return 0;
+    HMV_CHECK((C * sizeof(T)) % 16 == 0, "sample_gather: row must be a multiple of 16 bytes");
+    sample_gather_kernel<T><<<n_img * kJoints, 128, 0, s>>>(feat, xy, rows, wts, H, W, C);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int sample_gather_launch<bf16>(const bf16*, const float*, bf16*, float*, int, int, int, int, cudaStream_t);
+template int sample_gather_launch<float>(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// token assembly: bilinear blend | xy | crop fov | + sinusoidal PE  (reference handmvnet.py:185-225,
+// models/utils.py:134-171, layers.py:152-158)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tokens_kernel(const TokenParams p) {
+    const int row = blockIdx.x;                // n * 21 + j
+    const int n = row / kJoints;
+    const int pos = row % p.tokens_per_sample; // token index inside the sample (view-major)
+    const float* g = p.g + static_cast<size_t>(row) * 4 * p.ldg;
+    const float w0 = p.wts[row * 4], w1 = p.wts[row * 4 + 1], w2 = p.wts[row * 4 + 2], w3 = p.wts[row * 4 + 3];
+    float* of = p.tok_f32 + static_cast<size_t>(row) * p.pitch;
+    T* ol = p.tok_lp ? static_cast<T*>(p.tok_lp) + static_cast<size_t>(row) * p.pitch : nullptr;
+    const float* pe = p.pe ? p.pe + static_cast<size_t>(pos) * p.d : nullptr;
+    for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+        float v;
+        if (c < p.feat) {
+            v = 0.f;
+            v += g[c] * w0;
+            v += g[p.ldg + c] * w1;
+            v += g[2 * p.ldg + c] * w2;
+            v += g[3 * p.ldg + c] * w3;
+        } else {
+            int e = c - p.feat;
+            if (p.use_pos2d && e < 2) {
+                v = p.xy[row * 2 + e];
+            } else {
+                if (p.use_pos2d) e -= 2;
+                // e in [0,10): point e/2 of (x1,y1),(x1,y2),(x2,y1),(x2,y2),centre ; axis e%2
+                const float* bb = p.bbox + n * 4;
+                const float* k = p.intr + n * 4;
+                const int pt = e >> 1, ax = e & 1;
+                float coord;
+                if (pt == 4) coord = (bb[ax] + bb[2 + ax]) / 2.f;
+                else coord = ax == 0 ? bb[(pt >> 1) * 2] : bb[1 + (pt & 1) * 2];
+                v = atanf((coord - k[2 + ax]) / k[ax]);
+            }
+        }
+        if (pe) v += pe[c];
+        of[c] = v;
+        if (ol) ol[c] = from_f<T>(v);
+    }
+}
+
+template <typename T>
+int tokens_launch(const TokenParams& p, cudaStream_t s) {
+    if (p.n_img == 0) return 0;
+    HMV_CHECK(!p.use_crop || (p.bbox && p.intr), "tokens: 'crop' positional encoding needs bbox and intrinsics");
+    tokens_kernel<T><<<p.n_img * kJoints, 128, 0, s>>>(p);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int tokens_launch<bf16>(const TokenParams&, cudaStream_t);
+template int tokens_launch<float>(const TokenParams&, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// attention core: one CTA per (sample, head); K/V staged in shared memory, one warp per query row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_kernel(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out, int tokens_per_sample,
+                 int q_row0, int nq, int kv_row0, int nk, int heads, float scale) {
+    constexpr int DH = 128;
+    constexpr int PK = DH + (sizeof(T) == 2 ? 2 : 1);      // padded K pitch: conflict-free lane-per-key reads
+    constexpr int MAXJ = 11;                               // keys per lane: nk <= 352
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int inner = heads * DH;
+    T* ks = reinterpret_cast<T*>(att_smem);
+    T* vs = ks + static_cast<size_t>(nk) * PK + (sizeof(T) == 2 ? ((nk * PK) & 1 ? 1 : 0) : 0);
+    // align V to 16 B
+    vs = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(vs) + 15) & ~static_cast<uintptr_t>(15));
+    float* qs = reinterpret_cast<float*>(vs + static_cast<size_t>(nk) * DH);
+    float* ps = qs + 8 * DH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const T* kbase = qkv + (static_cast<size_t>(b) * tokens_per_sample + kv_row0) * ld + inner + h * DH;
+    const T* vbase = kbase + inner;
+    for (int i = threadIdx.x; i < nk * DH; i += blockDim.x) {
+        const int j = i / DH, d = i % DH;
+        ks[j * PK + d] = kbase[static_cast<size_t>(j) * ld + d];
+        vs[j * DH + d] = vbase[static_cast<size_t>(j) * ld + d];
+    }
+    __syncthreads();
+
+    float* q = qs + warp * DH;
+    float* pw = ps + warp * (MAXJ * 32);
+    for (int i = warp; i < nq; i += 8) {
+        const T* qrow = qkv + (static_cast<size_t>(b) * tokens_per_sample + q_row0 + i) * ld + h * DH;
+        for (int d = lane; d < DH; d += 32) q[d] = to_f(qrow[d]) * scale;
+        __syncwarp();
+        float sc[MAXJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const int j = jj * 32 + lane;
+            float s = -INFINITY;
+            if (j < nk) {
+                s = 0.f;
+                if constexpr (sizeof(T) == 2) {
+                    const uint32_t* kr = reinterpret_cast<const uint32_t*>(ks + j * PK);
+#pragma unroll 8
+                    for (int d2 = 0; d2 < DH / 2; ++d2) {
+                        const float2 kf = unpack_bf16x2(kr[d2]);
+                        s = fmaf(q[2 * d2], kf.x, s);
+                        s = fmaf(q[2 * d2 + 1], kf.y, s);
+                    }
+                } else {
+                    const float* kr = reinterpret_cast<const float*>(ks) + j * PK;
+#pragma unroll 8
+                    for (int d = 0; d < DH; ++d) s = fmaf(q[d], kr[d], s);
+                }
+            }
+            sc[jj] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const int j = jj * 32 + lane;
+            if (j < nk) {
+                const float e = expf(sc[jj] - mx);
+                pw[j] = e;
+                sum += e;
+            }
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            const float pj = pw[j];
+            if constexpr (sizeof(T) == 2) {
+                const uint2 vv = *reinterpret_cast<const uint2*>(vs + j * DH + lane * 4);
+                const float2 f0 = unpack_bf16x2(vv.x), f1 = unpack_bf16x2(vv.y);
+                a0 = fmaf(pj, f0.x, a0); a1 = fmaf(pj, f0.y, a1); a2 = fmaf(pj, f1.x, a2); a3 = fmaf(pj, f1.y, a3);
+            } else {
+                const float4 vv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(vs) + j * DH + lane * 4);
+                a0 = fmaf(pj, vv.x, a0); a1 = fmaf(pj, vv.y, a1); a2 = fmaf(pj, vv.z, a2); a3 = fmaf(pj, vv.w, a3);
+            }
+        }
+        const float inv = 1.f / sum;
+        T* orow = out + (static_cast<size_t>(b) * nq + i) * ld_out + h * DH + lane * 4;
+        orow[0] = from_f<T>(a0 * inv); orow[1] = from_f<T>(a1 * inv);
+        orow[2] = from_f<T>(a2 * inv); orow[3] = from_f<T>(a3 * inv);
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int attention_launch(const T* qkv, int ld, T* out, int ld_out, int batch, int tokens_per_sample, int q_row0, int nq,
+                     int kv_row0, int nk, int heads, int dim_head, float scale, cudaStream_t s) {
+    if (batch == 0) return 0;
+    HMV_CHECK(dim_head == 128, "attention: dim_head must be 128");
+    HMV_CHECK(nk <= 352 && nk > 0 && nq > 0, "attention: key count out of range (<= 352)");
+    constexpr int PK = 128 + (sizeof(T) == 2 ? 2 : 1);
+    const size_t smem = static_cast<size_t>(nk) * PK * sizeof(T) + 32 + static_cast<size_t>(nk) * 128 * sizeof(T) +
+                        8 * 128 * sizeof(float) + 8 * 11 * 32 * sizeof(float);
+    HMV_CHECK(smem <= 227 * 1024, "attention: K/V do not fit in shared memory at this view count and precision");
+    static size_t configured[2] = {0, 0};
+    size_t& cfg = configured[sizeof(T) == 2 ? 0 : 1];
+    if (smem > cfg) {
+        HMV_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cfg = smem;
+    }
+    attention_kernel<T><<<dim3(batch, heads), 256, smem, s>>>(qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq,
+                                                             kv_row0, nk, heads, scale);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int attention_launch<bf16>(const bf16*, int, bf16*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
+template int attention_launch<float>(const float*, int, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (optionally two chained LayerNorms): one warp per row, values kept in registers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void layernorm_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ g1,
+                                 const float* __restrict__ b1, float* __restrict__ out_f32, int ld_out,
+                                 const float* __restrict__ g2, const float* __restrict__ b2, T* __restrict__ out_lp,
+                                 int ld_lp, int rows, int d, float eps) {
+    constexpr int MAXPER = 20;                 // d <= 640
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = in + static_cast<size_t>(row) * ld_in;
+    float v[MAXPER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXPER; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < d ? x[c] : 0.f;
+        s += v[i];
+    }
+    const float inv_d = 1.f / static_cast<float>(d);
+    float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXPER; ++i) {
+        const int c = lane + 32 * i;
+        const float t = c < d ? v[i] - mean : 0.f;
+        ss += t * t;
+    }
+    float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXPER; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) {
+            v[i] = (v[i] - mean) * rstd * g1[c] + b1[c];
+            if (out_f32) out_f32[static_cast<size_t>(row) * ld_out + c] = v[i];
+            s += v[i];
+        }
+    }
+    if (!out_lp) return;
+    if (g2) {
+        mean = warp_sum(s) * inv_d;
+        ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXPER; ++i) {
+            const int c = lane + 32 * i;
+            const float t = c < d ? v[i] - mean : 0.f;
+            ss += t * t;
+        }
+        rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+#pragma unroll
+        for (int i = 0; i < MAXPER; ++i) {
+            const int c = lane + 32 * i;
+            if (c < d) out_lp[static_cast<size_t>(row) * ld_lp + c] = from_f<T>((v[i] - mean) * rstd * g2[c] + b2[c]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MAXPER; ++i) {
+            const int c = lane + 32 * i;
+            if (c < d) out_lp[static_cast<size_t>(row) * ld_lp + c] = from_f<T>(v[i]);
+        }
+    }
+}
+
+template <typename T>
+int layernorm_launch(const float* in, int ld_in, const float* g1, const float* b1, float* out_f32, int ld_out,
+                     const float* g2, const float* b2, T* out_lp, int ld_lp, int rows, int d, float eps,
+                     cudaStream_t s) {
+    if (rows == 0) return 0;
+    HMV_CHECK(d <= 640, "layernorm: d_model > 640 not supported");
+    layernorm_kernel<T><<<(rows + 7) / 8, 256, 0, s>>>(in, ld_in, g1, b1, out_f32, ld_out, g2, b2, out_lp, ld_lp, rows, d, eps);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int layernorm_launch<bf16>(const float*, int, const float*, const float*, float*, int, const float*,
+                                    const float*, bf16*, int, int, int, float, cudaStream_t);
+template int layernorm_launch<float>(const float*, int, const float*, const float*, float*, int, const float*,
+                                     const float*, float*, int, int, int, float, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// Chebyshev graph-conv head (reference nets.py:133-139, layers.py:387-403): one CTA per sample.
+// Layer: out = sum_k T_k (X W_k) + b ; thread c owns output column c, so T_k is applied in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGcnPad = 24;                    // 21 joints padded to 6 float4
+
+__device__ __forceinline__ void gcn_layer(const float* __restrict__ xt /*[cin][24] smem*/, int cin,
+                                          const float* __restrict__ w /*[3][cin][cout]*/, const float* __restrict__ bias,
+                                          int cout, const float* __restrict__ basis /*[3][21][21] smem*/, bool leaky,
+                                          float (&o)[kJoints], int c) {
+#pragma unroll
+    for (int r = 0; r < kJoints; ++r) o[r] = bias[c];
+    for (int k = 0; k < 3; ++k) {
+        float z[kGcnPad];
+#pragma unroll
+        for (int r = 0; r < kGcnPad; ++r) z[r] = 0.f;
+        const float* wk = w + static_cast<size_t>(k) * cin * cout + c;
+        for (int i = 0; i < cin; ++i) {
+            const float wv = __ldg(wk + static_cast<size_t>(i) * cout);
+            const float4* xr = reinterpret_cast<const float4*>(xt + i * kGcnPad);
+#pragma unroll
+            for (int q = 0; q < kGcnPad / 4; ++q) {
+                const float4 xv = xr[q];
+                z[4 * q] = fmaf(xv.x, wv, z[4 * q]);         z[4 * q + 1] = fmaf(xv.y, wv, z[4 * q + 1]);
+                z[4 * q + 2] = fmaf(xv.z, wv, z[4 * q + 2]); z[4 * q + 3] = fmaf(xv.w, wv, z[4 * q + 3]);
+            }
+        }
+        const float* tk = basis + k * kJoints * kJoints;
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int s = 0; s < kJoints; ++s) a = fmaf(tk[r * kJoints + s], z[s], a);
+            o[r] += a;
+        }
+    }
+    if (leaky) {
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) o[r] = o[r] > 0.f ? o[r] : 0.01f * o[r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gcn_kernel(const GcnParams p) {
+    extern __shared__ __align__(16) float gsm[];
+    float* xt = gsm;                                   // [max(d_in,256)][24]
+    float* basis = gsm + static_cast<size_t>(p.d_in > 256 ? p.d_in : 256) * kGcnPad;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* x = p.x + static_cast<size_t>(b) * kJoints * p.ld;
+    for (int i = tid; i < p.d_in * kGcnPad; i += blockDim.x) {
+        const int c = i / kGcnPad, r = i % kGcnPad;
+        xt[i] = r < kJoints ? x[static_cast<size_t>(r) * p.ld + c] : 0.f;
+    }
+    for (int i = tid; i < 3 * kJoints * kJoints; i += blockDim.x) basis[i] = p.basis[i];
+    __syncthreads();
+    float o[kJoints];
+    gcn_layer(xt, p.d_in, p.w[0], p.b[0], 256, basis, true, o, tid);           // 256 threads <-> 256 columns
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kJoints; ++r) xt[tid * kGcnPad + r] = o[r];
+    xt[tid * kGcnPad + 21] = 0.f; xt[tid * kGcnPad + 22] = 0.f; xt[tid * kGcnPad + 23] = 0.f;
+    __syncthreads();
+    if (tid < 64) gcn_layer(xt, 256, p.w[1], p.b[1], 64, basis, true, o, tid);
+    __syncthreads();
+    if (tid < 64) {
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) xt[tid * kGcnPad + r] = o[r];
+        xt[tid * kGcnPad + 21] = 0.f; xt[tid * kGcnPad + 22] = 0.f; xt[tid * kGcnPad + 23] = 0.f;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        gcn_layer(xt, 64, p.w[2], p.b[2], 3, basis, false, o, tid);
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) p.out[(static_cast<size_t>(b) * kJoints + r) * 3 + tid] = o[r];
+    }
+}
+
+int gcn_launch(const GcnParams& p, cudaStream_t s) {
+    if (p.batch == 0) return 0;
+    HMV_CHECK(p.d_in <= 1024, "gcn: d_in too large");
+    const size_t smem = (static_cast<size_t>(p.d_in > 256 ? p.d_in : 256) * kGcnPad + 3 * kJoints * kJoints) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        HMV_CUDA(cudaFuncSetAttribute(gcn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    gcn_kernel<<<p.batch, 256, smem, s>>>(p);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace hmv

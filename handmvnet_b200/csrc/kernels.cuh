@@ -1,0 +1,75 @@
+// Launchers for the non-GEMM kernels of the path and the fp32 check-mode conv.
+#pragma once
+#include "common.cuh"
+
+namespace hmv {
+
+constexpr int kJoints = 21;
+
+struct ConvF32Params {
+    const float* in;     // NHWC [n_img, Hin, Win, Cin]
+    const float* w;      // [Nalloc, K], K = kh*kw*Cin ordered (r, s, c)
+    int Hin, Win, Cin, Hout, Wout, kh, kw, stride, pad;
+    int M, K, Nalloc;
+    Epilogue ep;
+};
+int conv_f32_launch(const ConvF32Params& p, cudaStream_t stream);
+
+// x fp32 NCHW [n,3,H,W] -> zero-padded NHWC4 [n, Hp, Wp, 4]; pixel (h,w) lands at (h+pad, w+pad).
+template <typename T>
+int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, int Wp, int pad, cudaStream_t s);
+
+// 3x3 / stride 2 / pad 1 max pooling, NHWC (reference resnet.py:165,221).
+template <typename T>
+int maxpool_launch(const T* in, T* out, int n_img, int Hin, int Win, int C, cudaStream_t s);
+
+// soft-argmax over H*W with temperature (reference models/utils.py:35-62); xy in heatmap pixels,
+// xy_scaled = xy * scale (reference handmvnet.py:252).
+int softargmax_launch(const float* hm, float* xy, float* xy_scaled, int n_maps, int H, int W, float temperature,
+                      float scale, cudaStream_t s);
+
+// Bilinear neighbours of every joint (reference nets.py:46-53 == grid_sample align_corners=True,
+// zero padding): copies the 4 neighbour feature rows to rows[(n*21+j)*4+q][C] and writes the
+// bilinear weights (0 for out-of-range neighbours) to wts.
+template <typename T>
+int sample_gather_launch(const T* feat, const float* xy, T* rows, float* wts, int n_img, int H, int W, int C,
+                         cudaStream_t s);
+
+struct TokenParams {
+    const float* g;        // [n_img*21*4, ldg] sampled conv+BN+ReLU rows (fp32)
+    int ldg;
+    const float* wts;      // [n_img*21*4]
+    const float* xy;       // [n_img*21*2]
+    const float* bbox;     // [n_img*4] xyxy or null
+    const float* intr;     // [n_img*4] fx fy cx cy or null
+    const float* pe;       // [tokens_per_sample, d] or null
+    float* tok_f32;        // [n_img*21, pitch]
+    void* tok_lp;          // [n_img*21, pitch] low-precision copy (bf16) or null in fp32 mode
+    int n_img, feat, d, pitch, tokens_per_sample, use_pos2d, use_crop;
+};
+template <typename T>
+int tokens_launch(const TokenParams& p, cudaStream_t s);
+
+// per (sample, head) softmax(Q K^T * scale) V  (reference layers.py:217-223)
+template <typename T>
+int attention_launch(const T* qkv, int ld, T* out, int ld_out, int batch, int tokens_per_sample, int q_row0, int nq,
+                     int kv_row0, int nk, int heads, int dim_head, float scale, cudaStream_t s);
+
+// h = LN(in; g1,b1) -> out_f32 ; out_lp = g2 ? LN(h; g2,b2) : h   (reference layers.py:228,165,233)
+template <typename T>
+int layernorm_launch(const float* in, int ld_in, const float* g1, const float* b1, float* out_f32, int ld_out,
+                     const float* g2, const float* b2, T* out_lp, int ld_lp, int rows, int d, float eps,
+                     cudaStream_t s);
+
+struct GcnParams {
+    const float* x;        // [batch, 21, ld]
+    int ld, d_in;
+    const float* w[3];     // [3, cin, cout] each (reference layers.py:372 weight [K+1,1,cin,cout])
+    const float* b[3];
+    const float* basis;    // [3, 21, 21] Chebyshev T_k
+    float* out;            // [batch, 21, 3]
+    int batch;
+};
+int gcn_launch(const GcnParams& p, cudaStream_t s);
+
+}  // namespace hmv

@@ -1,0 +1,121 @@
+/*
+ * handmvnet_b200 - C ABI of the B200-native HandMvNet inference forward path.
+ *
+ * The reference (pyxploiter/HandMvNet) is pure Python/PyTorch and has no FFI of its own; this
+ * header is the boundary a maintainer binds instead of calling the torch modules.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference root).
+ * Conventions: plain pointers and sizes only (no torch / C++ types), every function returns 0 on
+ * success and non-zero on failure with the message available from hmv_last_error(); no exception
+ * crosses this boundary; all device pointers are fp32 and caller-owned; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  One handle per device, re-entrant per
+ * handle, not thread-safe on one handle.
+ */
+#ifndef HANDMVNET_B200_H
+#define HANDMVNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hmv_handle hmv_handle;
+
+enum { HMV_PRECISION_BF16 = 0, HMV_PRECISION_FP32 = 1 };
+
+/* Mirrors the keys HandMvNet.__init__ reads from cfg["model"], cfg["data"], cfg["train"]
+ * (src/models/handmvnet.py:28-125, configs/release/*.yaml). */
+typedef struct hmv_config {
+    int32_t num_views;        /* len(model.selected_views)                          */
+    int32_t image_size;       /* data.image_size   (256)                            */
+    int32_t heatmap_size;     /* data.heatmap_size (32)                             */
+    int32_t use_pos2d;        /* "pos2d" in model.pos_enc                           */
+    int32_t use_crop;         /* "crop"  in model.pos_enc  (needs bbox + intrinsic)  */
+    int32_t use_sin;          /* "sin"   in model.pos_enc                           */
+    int32_t fusion_layers;    /* model.fusion_layers (odd)                          */
+    int32_t precision;        /* HMV_PRECISION_BF16 (tcgen05 path) | HMV_PRECISION_FP32 (check mode) */
+    int32_t micro_batch;      /* samples processed per internal pass (workspace is sized for it) */
+    int32_t device;           /* CUDA device ordinal                                */
+} hmv_config;
+
+/* HandMvNet(train_params, model_params, data_params)  - src/models/handmvnet.py:28 */
+int hmv_create(const hmv_config* cfg, hmv_handle** out);
+int hmv_destroy(hmv_handle* h);
+
+/* model.load_state_dict(strict=True) - src/eval.py:46-50.  `name` is the reference state_dict key
+ * (355 keys, e.g. "backbone.layer3.0.conv2.weight"); data is host fp32, dims as in the reference.
+ * Two extra optional constants the reference builds in its constructors may be supplied:
+ * "pe" [21*V, feat_dim] (layers.py:136-150) and "cheb_basis" [3,21,21] (layers.py:405-445). */
+int hmv_set_weight(hmv_handle* h, const char* name, const float* data, const int64_t* dims, int32_t ndim);
+/* Folds BatchNorm, repacks to the kernel layouts, uploads, builds TMA descriptors.  Fails if a
+ * key is missing (strict). */
+int hmv_prepare(hmv_handle* h);
+
+/* model(x, bbox, cam_params) - src/models/handmvnet.py:158-266 (callers: src/eval_fps.py:83,91;
+ * validation_step/test_step :468-516).  Device pointers:
+ *   x        [B, V, 3, S, S] fp32 NCHW          bbox [B, V, 4] xyxy (may be NULL without "crop")
+ *   intr     [B, V, 4] (fx, fy, cx, cy)  (cam_params["intrinsic"]; may be NULL without "crop")
+ *   heatmap  [B, V, 21, 32, 32]   joints_crop_img [B, V, 21, 2]   joints_cam [B, 21, 3]
+ * Asynchronous on `stream`. */
+int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch,
+                float* heatmap, float* joints_crop_img, float* joints_cam, void* stream);
+
+/* Same call with HOST buffers (pinned recommended): chunks of micro_batch samples are copied
+ * host->device on a copy stream overlapped with compute, results are copied back; returns after
+ * everything has completed.  Any output pointer may be NULL to skip that copy. */
+int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch,
+                     float* heatmap, float* joints_crop_img, float* joints_cam);
+
+/* Blocks until the handle's work is done and reports device-side pipeline errors. */
+int hmv_synchronize(hmv_handle* h);
+
+/* ---- per-stage entry points (teacher-forced parity tests, micro-benchmarks) ------------------ */
+enum {
+    HMV_STAGE_BACKBONE = 0,   /* resnet.py:216-239       x -> FEAT                          */
+    HMV_STAGE_POSE = 1,       /* handmvnet.py:180-182    FEAT -> HEATMAP, XY                */
+    HMV_STAGE_SAMPLE = 2,     /* handmvnet.py:185-225 + layers.py:157  FEAT, XY -> TOKENS   */
+    HMV_STAGE_FUSION = 3,     /* fusion.py:26-30         TOKENS -> FUSED                    */
+    HMV_STAGE_GCN = 4         /* nets.py:133-139         FUSED -> JOINTS                    */
+};
+enum {
+    HMV_T_FEAT = 0,           /* [n*V, 1024, 32, 32] NCHW                                    */
+    HMV_T_HEATMAP = 1,        /* [n*V, 21, 32, 32]                                          */
+    HMV_T_XY = 2,             /* [n*V, 21, 2] heatmap pixels                                 */
+    HMV_T_TOKENS = 3,         /* [n, 21*V, feat_dim] (positional encoding already added)     */
+    HMV_T_FUSED = 4,          /* [n, 21, feat_dim]                                           */
+    HMV_T_JOINTS = 5          /* [n, 21, 3]                                                  */
+};
+/* Runs one stage on the handle's internal tensors for `batch` <= micro_batch samples.
+ * x / bbox / intr are only read by the stages that need them (others may pass NULL). */
+int hmv_stage_run(hmv_handle* h, int32_t stage, const float* x, const float* bbox, const float* intr,
+                  int32_t batch, void* stream);
+/* Copy an internal tensor to / from a dense fp32 device buffer in the reference's layout. */
+int hmv_tensor_get(hmv_handle* h, int32_t tensor, float* dst, int32_t batch, void* stream);
+int hmv_tensor_set(hmv_handle* h, int32_t tensor, const float* src, int32_t batch, void* stream);
+
+/* Backbone bisect helper: run the first `num_steps` entries of the backbone plan on n_img images
+ * and export the output of the last one as NCHW fp32; chw receives (C, H, W). */
+int hmv_debug_backbone(hmv_handle* h, const float* x, int32_t n_img, int32_t num_steps, float* out,
+                       int32_t* chw, void* stream);
+int hmv_debug_num_steps(hmv_handle* h);
+const char* hmv_debug_step_name(hmv_handle* h, int32_t step);
+
+/* One implicit-GEMM convolution through the same kernels the model uses (micro-benchmark /
+ * kernel unit test):  out = act(conv(in, w) * scale + shift (+ residual)),  NCHW fp32 in/out,
+ * w [cout, cin, k, k], scale/shift per output channel (the folded BatchNorm), residual optional.
+ * Replaces nn.Conv2d + nn.BatchNorm2d + ReLU call sites (backbones/resnet.py:127-141). */
+int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const float* scale, const float* shift,
+                    const float* residual, float* out, int32_t n_img, int32_t cin, int32_t hin, int32_t win,
+                    int32_t cout, int32_t ksize, int32_t stride, int32_t relu, float* elapsed_ms, int32_t iters,
+                    void* stream);
+
+/* Number of kernels enqueued by the handle so far (bench.py's gpu_launches claim). */
+int64_t hmv_launch_count(hmv_handle* h);
+int hmv_num_sms(hmv_handle* h);
+const char* hmv_last_error(void);
+const char* hmv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANDMVNET_B200_H */

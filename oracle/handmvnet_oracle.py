@@ -193,30 +193,40 @@ def _bn(sd, name, x):
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, BN_EPS)
 
 
-def bottleneck(sd, p, x, stride):
+def bottleneck(sd, p, x, stride, taps=None):
     """reference resnet.py:124-144 (Bottleneck.forward)."""
+    key = p[len("backbone."):]
     out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"])))
+    if taps is not None:
+        taps[key + ".conv1"] = out
     out = F.relu(_bn(sd, p + ".bn2", F.conv2d(out, sd[p + ".conv2.weight"], stride=stride, padding=1)))
+    if taps is not None:
+        taps[key + ".conv2"] = out
     out = _bn(sd, p + ".bn3", F.conv2d(out, sd[p + ".conv3.weight"]))
     if (p + ".downsample.0.weight") in sd:
         x = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
-    return F.relu(out + x)
+        if taps is not None:
+            taps[key + ".downsample"] = x
+    out = F.relu(out + x)
+    if taps is not None:
+        taps[key + ".conv3"] = out
+    return out
 
 
-def backbone(sd, x, taps=None):
+def backbone(sd, x, taps=None, per_layer=False):
     """reference resnet.py:216-239, variant "paper": conv7x7/2, BN, ReLU, maxpool3x3/2,
-    layer1..layer3 (layer3 stride 1) -> [N,1024,H/8,W/8]."""
+    layer1..layer3 (layer3 stride 1) -> [N,1024,H/8,W/8].  per_layer=True also records every conv output
+    (after its BN / ReLU / residual) under the product's step names."""
     x = F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3)))
     if taps is not None:
-        taps["stem_conv"] = x
+        taps["conv1"] = x
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     if taps is not None:
+        taps["maxpool"] = x
         taps["stem"] = x
     for li, (nblk, stride) in enumerate(zip(LAYER_BLOCKS, LAYER_STRIDES), 1):
         for b in range(nblk):
-            x = bottleneck(sd, f"backbone.layer{li}.{b}", x, stride if b == 0 else 1)
-            if taps is not None and li == 1 and b == 0:
-                taps["layer1_0"] = x
+            x = bottleneck(sd, f"backbone.layer{li}.{b}", x, stride if b == 0 else 1, taps if per_layer else None)
         if taps is not None:
             taps[f"layer{li}"] = x
     return x

@@ -1,0 +1,248 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against the CPU oracle
+(oracle/handmvnet_oracle.py, itself pinned to the reference by tests/golden/*.npz).
+
+Tolerances (BASELINE.json north_star): fp32 check mode <= 1e-4 relative per stage and final keypoints within
+0.1 mm; bf16 tensor-core mode <= 1e-2 relative per stage with TEACHER FORCING (each stage is fed the oracle's
+upstream tensors, because soft-argmax at temperature 1000 makes the end-to-end map discontinuous).
+"relative" is the relative L2 error ||a-b|| / ||b|| over the stage tensor.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import handmvnet_oracle as O
+from gpu_util import build_pair, conv_bn_act, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the implicit-GEMM conv kernel alone (every geometry class of SURVEY.md appendix A)
+# ---------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # cin, cout, k, stride, H,  W,  residual
+    (64, 64, 1, 1, 64, 64, False),
+    (64, 256, 1, 1, 64, 64, True),
+    (256, 128, 1, 1, 64, 64, False),
+    (64, 64, 3, 1, 64, 64, False),
+    (128, 128, 3, 1, 32, 32, False),
+    (256, 256, 3, 1, 32, 32, False),
+    (128, 128, 3, 2, 64, 64, False),
+    (256, 512, 1, 2, 64, 64, False),
+    (1024, 256, 1, 1, 32, 32, False),
+    (256, 1024, 1, 1, 32, 32, True),
+    (512, 21, 1, 1, 32, 32, False),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_bn_act_kernel(case, precision):
+    cin, cout, k, stride, h, w, use_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    n = 3                                            # odd image count: exercises ragged tile counts
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(n, cout, h // stride, w // stride, generator=g) if use_res else None
+    if precision == "bf16":                          # compare against the same bf16-rounded operands
+        x = x.bfloat16().float()
+        res = res.bfloat16().float() if use_res else None
+        wq = (wt * scale[:, None, None, None]).bfloat16().float()
+        ref = F.conv2d(x, wq, stride=stride, padding=k // 2) + shift[None, :, None, None]
+    else:
+        ref = F.conv2d(x, wt, stride=stride, padding=k // 2) * scale[None, :, None, None] + shift[None, :, None, None]
+    if use_res:
+        ref = ref + res
+    ref = F.relu(ref)
+    out, _ = conv_bn_act(precision, x.cuda(), wt.cuda(), scale.cuda(), shift.cuda(), res.cuda() if use_res else None,
+                         stride=stride, relu=True)
+    err = rel_l2(out, ref)
+    assert err < (5e-3 if precision == "bf16" else 1e-5), f"{case} {precision}: rel-L2 {err:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole path, fp32 check mode
+# ---------------------------------------------------------------------------------------------------
+def _forward(m, x, bbox, intr, crop=True):
+    if crop:
+        out = m(x.cuda(), bbox.cuda(), {"intrinsic": intr.cuda()})
+    else:
+        out = m(x.cuda())
+    m.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("views,crop,seed", [(5, True, 0), (8, True, 2), (5, False, 3)])
+def test_fp32_end_to_end_matches_oracle(views, crop, seed):
+    m, ocfg, sd = build_pair(views, crop, "fp32", micro_batch=2, seed=seed)
+    x, bbox, intr = O.make_inputs(2, views, seed=100 + seed)
+    ref, taps = O.forward(sd, ocfg, x, bbox if crop else None, intr if crop else None, return_taps=True)
+    out = _forward(m, x, bbox, intr, crop)
+    assert out["heatmap"].shape == ref["heatmap"].shape and out["joints_cam"].shape == ref["joints_cam"].shape
+    assert rel_l2(out["heatmap"], ref["heatmap"]) < TOL["fp32"]
+    # stage tensors of the same run
+    assert rel_l2(m.tensor_get("feat", 2), taps["backbone_out"]) < TOL["fp32"]
+    assert rel_l2(m.tensor_get("tokens", 2), taps["tokens_pe"]) < 5 * TOL["fp32"]
+    assert rel_l2(m.tensor_get("fused", 2), taps["fused"]) < 5 * TOL["fp32"]
+    assert (out["joints_crop_img"] - ref["joints_crop_img"]).abs().max() < 0.05          # crop-image pixels
+    err_mm = (out["joints_cam"] - ref["joints_cam"]).abs().max().item() * 1e3
+    assert err_mm < 0.1, f"final keypoints differ by {err_mm} mm"
+    assert rel_l2(out["joints_cam"], ref["joints_cam"]) < 1e-3
+
+
+def test_fp32_matches_reference_golden_fixtures(golden_dir):
+    """Directly against the fixtures the real reference produced (tests/golden, oracle/gen_golden.py)."""
+    for path in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+        g = np.load(path)
+        views, crop, b = int(g["meta_num_views"]), bool(g["meta_crop"]), int(g["meta_batch"])
+        m, ocfg, sd = build_pair(views, crop, "fp32", micro_batch=b, seed=int(g["meta_seed_w"]),
+                                 randomize_norm=bool(g["meta_randomize_norm"]))
+        x, bbox, intr = O.make_inputs(b, views, seed=int(g["meta_seed_x"]))
+        out = _forward(m, x, bbox, intr, crop)
+        assert np.abs(out["joints_cam"].numpy() - g["out_joints_cam"]).max() * 1e3 < 0.1, path
+        np.testing.assert_allclose(out["heatmap"][..., ::4, ::4].numpy(), g["out_heatmap_sub"], rtol=2e-3, atol=2e-3)
+        assert (out["heatmap"].flatten(-2).argmax(-1).numpy() == g["out_heatmap_argmax"]).mean() > 0.99, path
+        del m
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16 tensor-core path: teacher-forced per-stage parity
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_stagewise_teacher_forced(precision):
+    views, b = 5, 2
+    m, ocfg, sd = build_pair(views, True, precision, micro_batch=b, seed=0)
+    x, bbox, intr = O.make_inputs(b, views, seed=1234)
+    ref, taps = O.forward(sd, ocfg, x, bbox, intr, return_taps=True)
+    tol = TOL[precision]
+    report = {}
+    # backbone: x -> feat
+    m.stage_run("backbone", b, x=x.reshape(-1, 3, 256, 256).cuda())
+    report["backbone"] = rel_l2(m.tensor_get("feat", b), taps["backbone_out"])
+    # pose: oracle feat -> heatmap, xy
+    m.tensor_set("feat", taps["backbone_out"].cuda(), b)
+    m.stage_run("pose", b)
+    hm = m.tensor_get("heatmap", b).cpu()
+    report["heatmap"] = rel_l2(hm, taps["heatmap"])
+    xy_from_oracle_hm = O.soft_argmax_2d(hm)         # soft-argmax kernel checked on ITS OWN heatmap
+    report["xy_kernel"] = float((m.tensor_get("xy", b).cpu() - xy_from_oracle_hm).abs().max())
+    # sample + tokens: oracle feat + oracle xy -> tokens(+PE)
+    m.tensor_set("xy", taps["coords"].cuda(), b)
+    m.stage_run("sample", b, bbox=bbox.reshape(-1, 4).cuda(), intr=intr.reshape(-1, 4).cuda())
+    report["tokens"] = rel_l2(m.tensor_get("tokens", b), taps["tokens_pe"])
+    # fusion: oracle tokens -> fused
+    m.tensor_set("tokens", taps["tokens_pe"].cuda(), b)
+    m.stage_run("fusion", b)
+    report["fused"] = rel_l2(m.tensor_get("fused", b), taps["fused"])
+    # gcn: oracle fused -> joints
+    m.tensor_set("fused", taps["fused"].cuda(), b)
+    m.stage_run("gcn", b)
+    j = m.tensor_get("joints", b).cpu()
+    report["joints_rel"] = rel_l2(j, taps["joints_cam"])
+    report["joints_mm"] = float((j - taps["joints_cam"]).abs().max()) * 1e3
+    m.synchronize()
+    print(f"\n[{precision}] teacher-forced stage errors: " + ", ".join(f"{k}={v:.3e}" for k, v in report.items()))
+    assert report["backbone"] < tol
+    assert report["heatmap"] < tol
+    assert report["xy_kernel"] < 1e-3
+    assert report["tokens"] < tol
+    assert report["fused"] < tol
+    assert report["joints_rel"] < (1e-4 if precision == "fp32" else 1e-5) * 10   # GCN runs in fp32 in both modes
+    assert report["joints_mm"] < 0.1
+
+
+def test_bf16_end_to_end_is_close_where_argmax_agrees():
+    """End-to-end bf16: finite outputs, heatmaps within tolerance, and final keypoints within 0.1 mm for the
+    samples whose 2D argmax agrees with the oracle on every joint (SURVEY.md §7 'hard parts')."""
+    views, b = 5, 2
+    m, ocfg, sd = build_pair(views, True, "bf16", micro_batch=b, seed=1, randomize_norm=False)
+    x, bbox, intr = O.make_inputs(b, views, seed=77)
+    ref = O.forward(sd, ocfg, x, bbox, intr)
+    out = _forward(m, x, bbox, intr)
+    for v in out.values():
+        assert torch.isfinite(v).all()
+    assert rel_l2(out["heatmap"], ref["heatmap"]) < 2e-2
+    same = ((out["joints_crop_img"] - ref["joints_crop_img"]).abs().amax(dim=(1, 2, 3)) < 1.0)
+    flips = float(((out["joints_crop_img"] - ref["joints_crop_img"]).abs().amax(-1) >= 1.0).float().mean())
+    print(f"\n[bf16] e2e joint flip rate vs fp32 oracle: {flips:.3f} (reference's own bf16 autocast: 0.13)")
+    for i in range(b):
+        if same[i]:
+            assert (out["joints_cam"][i] - ref["joints_cam"][i]).abs().max() * 1e3 < 0.1
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at larger sizes (the oracle is too slow there)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_micro_batching_and_host_path_are_consistent(precision):
+    """Results must not depend on how the batch is chunked, on batch position, or on the host-buffer entry point."""
+    views = 5
+    b = 5 if precision == "bf16" else 3
+    m_small, ocfg, sd = build_pair(views, True, precision, micro_batch=2, seed=5)
+    m_big, _, _ = build_pair(views, True, precision, micro_batch=8, seed=5)
+    x, bbox, intr = O.make_inputs(b, views, seed=9)
+    a = _forward(m_small, x, bbox, intr)
+    c = _forward(m_big, x, bbox, intr)
+    for k in a:
+        assert torch.equal(a[k], c[k]), f"{k}: chunked (micro_batch=2) and unchunked results differ"
+    # permutation equivariance over samples
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(0))
+    p = _forward(m_big, x[perm], bbox[perm], intr[perm])
+    for k in a:
+        assert torch.equal(p[k], c[k][perm]), k
+    # host-buffer entry point (pinned memory, pipelined copies)
+    hcpu = m_small.forward_host(x.pin_memory(), bbox.pin_memory(), {"intrinsic": intr.pin_memory()})
+    for k in a:
+        assert torch.equal(hcpu[k], a[k]), k
+    # empty batch
+    e = m_big(x[:0].cuda(), bbox[:0].cuda(), {"intrinsic": intr[:0].cuda()})
+    assert e["joints_cam"].shape == (0, 21, 3)
+
+
+def test_bf16_matches_fp32_check_mode_at_batch_16():
+    """bf16 path against the on-device fp32 check mode at a size the CPU oracle is not run at:
+    heatmaps within the bf16 tolerance."""
+    views, b = 5, 16
+    mb, ocfg, sd = build_pair(views, True, "bf16", micro_batch=16, seed=7)
+    mf, _, _ = build_pair(views, True, "fp32", micro_batch=4, seed=7)
+    x, bbox, intr = O.make_inputs(b, views, seed=21)
+    ob = _forward(mb, x, bbox, intr)
+    of = _forward(mf, x, bbox, intr)
+    assert rel_l2(ob["heatmap"], of["heatmap"]) < 2e-2
+    assert torch.isfinite(ob["joints_cam"]).all()
+
+
+def test_known_answers_on_device():
+    """soft-argmax of a one-hot heatmap is that pixel; GCN of zeros is the bias path; tokens at integer
+    coordinates equal conv+BN+ReLU of that pixel (reference tests do not exist: SURVEY.md §4 item 2)."""
+    m, ocfg, sd = build_pair(5, True, "fp32", micro_batch=1, seed=0)
+    hm = torch.full((5, 21, 32, 32), -1.0)
+    for n in range(5):
+        for j in range(21):
+            hm[n, j, (3 * j + n) % 32, (5 * j + 2 * n) % 32] = 1.0
+    m.tensor_set("heatmap", hm.cuda(), 1)
+    # run only the soft-argmax by re-running the pose stage on a feature map would overwrite hm; use the oracle identity instead
+    xy_ref = O.soft_argmax_2d(hm)
+    exp = torch.tensor([[[(5 * j + 2 * n) % 32, (3 * j + n) % 32] for j in range(21)] for n in range(5)], dtype=torch.float32)
+    assert torch.allclose(xy_ref, exp, atol=1e-4)
+    # sampling at integer coordinates == per-pixel conv+BN+ReLU
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(5, 1024, 32, 32, generator=g)
+    m.tensor_set("feat", feat.cuda(), 1)
+    m.tensor_set("xy", exp.cuda(), 1)
+    x, bbox, intr = O.make_inputs(1, 5, seed=1)
+    m.stage_run("sample", 1, bbox=bbox.reshape(-1, 4).cuda(), intr=intr.reshape(-1, 4).cuda())
+    tok = m.tensor_get("tokens", 1).cpu() - O.positional_table(524, 105)[None]
+    dense = F.relu(O._bn(sd, "sample_nets.0.conv.1", F.conv2d(feat, sd["sample_nets.0.conv.0.weight"], sd["sample_nets.0.conv.0.bias"])))
+    want = torch.stack([torch.stack([dense[n, :, int(exp[n, j, 1]), int(exp[n, j, 0])] for j in range(21)]) for n in range(5)])
+    assert rel_l2(tok[0, :, :512], want.reshape(105, 512)) < 1e-4
+    assert torch.allclose(tok[0, :, 512:514], exp.reshape(105, 2), atol=1e-4)
+    assert torch.allclose(tok[0, :, 514:], O.crop_fov(bbox, intr).repeat_interleave(21, 0), atol=1e-5)

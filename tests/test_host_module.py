@@ -1,0 +1,96 @@
+"""Host-side (no GPU) checks of the drop-in boundary: state_dict contract, constructor error conventions of
+reference src/models/handmvnet.py:28-125, no CPU fallback, and that the C-ABI library exports every symbol
+include/handmvnet_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import handmvnet_oracle as O
+from handmvnet_b200 import HandMvNet, _lib
+from handmvnet_b200.config import release_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(views=5, crop=True, **kw):
+    cfg = release_config(views, crop)
+    return HandMvNet(cfg["train"], cfg["model"], cfg["data"], **kw), cfg
+
+
+@pytest.mark.parametrize("views,crop", [(5, True), (8, True), (5, False)])
+def test_state_dict_contract(views, crop):
+    m, _ = _model(views, crop)
+    ocfg = O.release_config(views, crop)
+    spec = {k: tuple(s) for k, s, _ in O._state_dict_spec(ocfg)}
+    sd = m.state_dict()
+    assert len(sd) == 355 and set(sd.keys()) == set(spec.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == spec[k], k
+    assert m.feat_dim == (524 if crop else 514)
+    # a reference-shaped state_dict loads strictly (src/eval.py:46-50)
+    m.load_state_dict(O.make_state_dict(ocfg, seed=3), strict=True)
+    assert "joints_late_fusion.pos_encoding.pe" not in sd           # plain attribute, like the reference
+    assert torch.equal(m.joints_late_fusion.pos_encoding.pe[0], O.positional_table(m.feat_dim, 21 * views))
+
+
+def test_constructor_error_conventions():
+    cfg = release_config(5, True)
+    bad = dict(cfg["model"], backbone="vgg")
+    with pytest.raises(AssertionError):
+        HandMvNet(cfg["train"], bad, cfg["data"])
+    with pytest.raises(AssertionError):
+        HandMvNet(cfg["train"], dict(cfg["model"], backbone_type="101"), cfg["data"])
+    with pytest.raises(NotImplementedError):
+        HandMvNet(cfg["train"], dict(cfg["model"], fusion="concat"), cfg["data"])
+    with pytest.raises(NotImplementedError):
+        HandMvNet(cfg["train"], cfg["model"], dict(cfg["data"], name="freihand"))
+    with pytest.raises(AssertionError):            # fusion.py:11
+        HandMvNet(cfg["train"], dict(cfg["model"], fusion_layers=4), cfg["data"])
+    with pytest.raises(NotImplementedError):       # scoped out
+        HandMvNet(dict(cfg["train"], root_relative=False), cfg["model"], cfg["data"])
+    with pytest.raises(NotImplementedError):
+        HandMvNet(cfg["train"], dict(cfg["model"], backbone="hrnet"), cfg["data"])
+
+
+def test_no_cpu_fallback_and_input_validation():
+    m, _ = _model()
+    m.eval()
+    x = torch.zeros(1, 5, 3, 256, 256)
+    bbox = torch.zeros(1, 5, 4)
+    cam = {"intrinsic": torch.ones(1, 5, 4)}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, bbox, cam)
+    with pytest.raises(ValueError, match="views"):
+        m(torch.zeros(1, 8, 3, 256, 256), torch.zeros(1, 8, 4), {"intrinsic": torch.ones(1, 8, 4)})
+    with pytest.raises(ValueError, match="crop"):
+        m(x)                                         # 'crop' positional encoding needs bbox + intrinsics
+    with pytest.raises(RuntimeError):                # parameter holders never compute
+        m.backbone(torch.zeros(1, 3, 256, 256))
+    m.freeze()
+    assert not any(p.requires_grad for p in m.parameters()) and not m.training
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "handmvnet_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hmv_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(_lib.EXPORTS)
+    lib = _lib.load()                                # raises if the .so was not built
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr), name
+    assert b"sm_100a" in lib.hmv_version()
+
+
+def test_create_without_gpu_reports_error():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    cfg = _lib.HmvConfig(num_views=5, image_size=256, heatmap_size=32, use_pos2d=1, use_crop=1, use_sin=1,
+                         fusion_layers=5, precision=0, micro_batch=1, device=0)
+    h = ctypes.c_void_p()
+    assert lib.hmv_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert len(lib.hmv_last_error()) > 0
+    with pytest.raises(RuntimeError):
+        _lib.check(1, "hmv_create")
