@@ -77,7 +77,7 @@ conv_f32_kernel(const ConvF32Params p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = n0 + tx * 4 + j;
-            if (col >= p.Nalloc) continue;
+            if (col >= ep.N) continue;
             float v = acc[i][j] + ep.bias[col];
             if (ep.res_mode == RES_F32) v += static_cast<const float*>(ep.residual)[rrow * ep.res_ld + col];
             if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
@@ -85,7 +85,7 @@ conv_f32_kernel(const ConvF32Params p) {
             if (ep.out_mode == OUT_F32_ROWMAJOR) {
                 static_cast<float*>(ep.out)[static_cast<size_t>(row) * ep.ldc + col] = v;
             } else if (ep.out_mode == OUT_F32_NCHW) {
-                if (col < ep.N) {
+                {
                     const int im = row / ep.hw, pix = row % ep.hw;
                     static_cast<float*>(ep.out)[(static_cast<size_t>(im) * ep.N + col) * ep.hw + pix] = v;
                 }

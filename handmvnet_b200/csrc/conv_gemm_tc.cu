@@ -41,7 +41,8 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
         for (int i = 0; i < 64; ++i)
             if (mbar_try_wait(bar, parity)) return true;
         if (clock64() - t0 > 4000000000LL) {
-            atomicExch(err_flag, code);
+            *reinterpret_cast<volatile int*>(err_flag) = code;     // mapped host memory: visible without a sync
+            __threadfence_system();
             return false;
         }
     }

@@ -238,6 +238,9 @@ static int finish_layer(hmv_handle* h, Layer& L, const std::vector<float>& wmat,
     if (upload_weights(h, &L.w, wp)) return 1;
     if (upload_f32(h, &L.bias, bp)) return 1;
     L.ep.bias = L.bias;
+    L.ep.N = L.cout;
+    HMV_CHECK(!h->bf16 || L.ep.out_mode == OUT_F32_NCHW || L.ep.ldc >= L.n_alloc,
+              "row-major output pitch must cover the padded tile width in " + L.name);
     return 0;
 }
 
@@ -349,7 +352,7 @@ static Epilogue make_ep(void* out, int ldc, int out_mode, int act) {
 // A conv layer from already-folded weights wf[cout][k*k][cin], bf[cout].  in: NHWC activations.
 static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vector<float>& wf, const std::vector<float>& bf,
                         int cin, int cout, int k, int stride, int hin, int win, const void* in, void* out, int act,
-                        const void* residual, int* index) {
+                        const void* residual, int* index, int nchw_hw = 0) {
     Layer L;
     L.name = name;
     L.cin = cin; L.cout = cout; L.ksize = k; L.stride = stride; L.pad = k / 2;
@@ -368,6 +371,7 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
     L.n_alloc = (cout + L.bn - 1) / L.bn * L.bn;
     if (!h->bf16) L.n_alloc = (cout + 3) / 4 * 4;
     L.ep = make_ep(out, cout, h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR, act);
+    if (nchw_hw > 0) { L.ep.out_mode = OUT_F32_NCHW; L.ep.hw = nchw_hw; }     // fp32 [n_img, cout, hw] output
     if (residual) {
         L.ep.residual = residual; L.ep.res_mode = h->bf16 ? RES_BF16 : RES_F32; L.ep.res_ld = cout;
     }
@@ -539,10 +543,10 @@ static int build_heads(hmv_handle* h) {
     const int lp_out = h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR;
     // ---- pose_net (layers.py:318-334 via handmvnet.py:71) ----
     if (add_conv(h, "pose_net.0", "pose_net.0", "pose_net.1", true, 1024, 512, 1, 1, h->hm, h->hm, h->featbuf, h->bufT1, ACT_RELU, nullptr, &h->pose0)) return 1;
-    if (add_conv(h, "pose_net.3", "pose_net.3", "", true, 512, kJoints, 1, 1, h->hm, h->hm, h->bufT1, h->hm_int, ACT_NONE, nullptr, &h->pose3)) return 1;
     {
-        Layer& L = h->layers[h->pose3];
-        L.ep.out_mode = OUT_F32_NCHW; L.ep.N = kJoints; L.ep.hw = hw;
+        std::vector<float> wf, bf;
+        if (fold_conv(h, "pose_net.3", "", true, kJoints, 512, 1, wf, bf)) return 1;
+        if (add_conv_raw(h, "pose_net.3", wf, bf, 512, kJoints, 1, 1, h->hm, h->hm, h->bufT1, h->hm_int, ACT_NONE, nullptr, &h->pose3, hw)) return 1;
     }
     // ---- SampleNet conv on gathered rows (nets.py:55-63; SURVEY appendix D identity) ----
     {
@@ -1126,7 +1130,13 @@ int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const fl
             if (residual) hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(out_elems), 256, 0, s>>>(residual, static_cast<float*>(dres), cout, hout * wout, out_elems);
         }
         int idx = -1;
-        if (hmv::add_conv_raw(h, "unit_conv", wf, sh, cin, cout, ksize, stride, hin, win, din, dout, relu ? hmv::ACT_RELU : hmv::ACT_NONE, dres, &idx)) break;
+        const bool direct_nchw = cout % 16 != 0;       // narrow heads (pose_net.3): fp32 NCHW epilogue straight into `out`
+        if (direct_nchw && residual) { hmv::set_error("hmv_conv_bn_act: residual needs cout % 16 == 0"); break; }
+        if (direct_nchw) {
+            if (hmv::add_conv_raw(h, "unit_conv", wf, sh, cin, cout, ksize, stride, hin, win, din, out, relu ? hmv::ACT_RELU : hmv::ACT_NONE, nullptr, &idx, /*nchw_hw=*/hout * wout)) break;
+        } else {
+            if (hmv::add_conv_raw(h, "unit_conv", wf, sh, cin, cout, ksize, stride, hin, win, din, dout, relu ? hmv::ACT_RELU : hmv::ACT_NONE, dres, &idx)) break;
+        }
         if (hmv::run_layer(h, h->layers[idx], n_img, s)) break;
         if (elapsed_ms && iters > 0) {
             cudaEvent_t e0, e1;
@@ -1142,7 +1152,8 @@ int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const fl
             cudaEventDestroy(e0); cudaEventDestroy(e1);
             if (!ok) break;
         }
-        if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(out_elems), 256, 0, s>>>(static_cast<const hmv::bf16*>(dout), out, cout, hout * wout, out_elems);
+        if (direct_nchw) { /* already written in the caller's layout */ }
+        else if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(out_elems), 256, 0, s>>>(static_cast<const hmv::bf16*>(dout), out, cout, hout * wout, out_elems);
         else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(out_elems), 256, 0, s>>>(static_cast<const float*>(dout), out, cout, hout * wout, out_elems);
         if (cudaStreamSynchronize(s) != cudaSuccess) { hmv::set_error(std::string("hmv_conv_bn_act: ") + cudaGetErrorString(cudaGetLastError())); break; }
         if (hmv::check_flag(h)) break;

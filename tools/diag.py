@@ -81,13 +81,21 @@ def backbone_bisect(precision):
 
 
 def main():
-    log("device:", torch.cuda.get_device_name(0))
+    phase = sys.argv[1] if len(sys.argv) > 1 else "all"
+    global LOG
+    LOG.close()
+    LOG = open(os.path.join(ROOT, "gpurun_out", f"diag_{phase}.txt"), "w")
+    log("device:", torch.cuda.get_device_name(0), "phase:", phase)
+    cases = [(64, 64, 1, 1, 64, 64), (128, 128, 1, 1, 32, 32), (1024, 256, 1, 1, 32, 32), (256, 1024, 1, 1, 32, 32),
+             (512, 21, 1, 1, 32, 32), (64, 64, 3, 1, 64, 64), (128, 128, 3, 1, 32, 32), (256, 256, 3, 1, 32, 32),
+             (128, 128, 3, 2, 64, 64), (256, 512, 1, 2, 64, 64)]
     for prec in ("fp32", "bf16"):
-        for case in [(64, 64, 1, 1, 64, 64), (128, 128, 1, 1, 32, 32), (1024, 256, 1, 1, 32, 32), (256, 1024, 1, 1, 32, 32),
-                     (512, 21, 1, 1, 32, 32), (64, 64, 3, 1, 64, 64), (128, 128, 3, 1, 32, 32), (256, 256, 3, 1, 32, 32),
-                     (128, 128, 3, 2, 64, 64), (256, 512, 1, 2, 64, 64)]:
-            conv_diag(prec, *case)
+        if phase in ("all", "conv_" + prec):
+            for case in cases:
+                conv_diag(prec, *case)
     for prec in ("fp32", "bf16"):
+        if phase not in ("all", "model_" + prec):
+            continue
         log(f"--- backbone bisect {prec} ---")
         r = backbone_bisect(prec)
         if r is None:
