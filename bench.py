@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py - multi-view hand poses/sec of the HandMvNet forward path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+Own arm.  A "step" is one forward of the release HO3D configuration (5 views, 256x256 crops, ResNet-50-paper
+backbone -> cross-attention fusion -> Chebyshev GCN head) over a synthetic batch of B=64 samples per GPU
+(BASELINE.json configs[1]; weak scaling: every rank gets its own 64 samples, no data-path collective, only an
+NCCL all-gather of the [B,21,3] poses).  `value` = samples all ranks processed / max-over-ranks device time with
+the inputs resident in HBM; `e2e` = the same through `HandMvNet.forward_host` (hmv_forward_host) with pinned
+HOST buffers, host->device copies of the step's inputs and device->host copies of the poses inside the timed
+region.  `roofline` describes the dominant kernel (the tcgen05 implicit-GEMM conv), timed per launch with CUDA
+events on its stream in a second pass over the same steps; `cpu_baseline` is the CPU oracle (a port of the
+reference's torch forward) timed on this box's host cores on a bounded sample.
+
+Reference arm (`--impl reference`): the reference's algorithm on the host CPU cores (oracle port, all threads),
+same metric / config, each step a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "multi-view hand poses/sec (HandMvNet forward, HO3D release config, 5 views)"
+UNIT = "poses/s"
+FLOP_PER_SAMPLE_V5 = 108.515e9        # SURVEY.md §8d (FlopCounterMode over the reference forward)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons, power = [], 0.0, set(), 0.0
+        for r in self.rows:
+            try:
+                clk, cmax, pw = float(r[1]), float(r[2]), float(r[3])
+            except (ValueError, IndexError):
+                continue
+            mx = max(mx, cmax)
+            power = max(power, pw)
+            if pw > 250:                       # under load
+                sm.append(clk)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "power_w_max": power, "samples": len(self.rows), "samples_under_load": len(sm)}
+
+
+def cpu_oracle_throughput(batch, iters, warmup, views=5):
+    """The CPU oracle (port of the reference's torch forward) on all host threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import handmvnet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.release_config(views, True)
+    sd = O.make_state_dict(cfg, seed=0, randomize_norm=False)
+    x, bbox, intr = O.make_inputs(batch, views, seed=1234)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        O.forward(sd, cfg, x, bbox, intr)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times) * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 2
+    ps, ms, cores = cpu_oracle_throughput(sample_b, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HO3D_HandMvNet release config, 5 views, B=64/GPU (reference CPU forward timed on a "
+                               f"bounded sample of B={sample_b} per step)", "views": 5, "image": 256},
+        "cpu_baseline": {"value": ps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle/handmvnet_oracle.py forward, B={sample_b} x {args.steps} steps, fp32, all host threads"},
+        "e2e": {"value": ps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from handmvnet_b200 import HandMvNet
+    from handmvnet_b200.config import release_config
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    views, B = 5, args.batch
+    cfg = release_config(views, True)
+    torch.manual_seed(0)
+    model = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision="bf16", micro_batch=args.micro_batch)
+    model.to(dev).eval()
+    model.freeze()
+    model.prepare(dev)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, views, 3, 256, 256, generator=g).pin_memory()            # 251 MB at B=64 (> 126 MB L2)
+    c = torch.rand(B, views, 2, generator=g) * torch.tensor([320.0, 240.0]) + torch.tensor([160.0, 120.0])
+    side = 100 + 150 * torch.rand(B, views, 1, generator=g)
+    bbox_host = torch.cat([c - side / 2, c + side / 2], dim=-1).pin_memory()
+    f = 500 + 200 * torch.rand(B, views, 1, generator=g)
+    intr_host = torch.cat([f, f, torch.full((B, views, 1), 320.0), torch.full((B, views, 1), 240.0)], dim=-1).pin_memory()
+    x, bbox, intr = x_host.to(dev), bbox_host.to(dev), intr_host.to(dev)
+    cam = {"intrinsic": intr}
+    gathered = [torch.empty(B, 21, 3, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        out = model(x, bbox, cam)
+        if world > 1:
+            dist.all_gather(gathered, out["joints_cam"])       # optional NCCL gather of the poses (252 B/sample)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = model.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(out["joints_cam"]).all()
+
+    # ---- end to end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
+    cam_host = {"intrinsic": intr_host}
+    for _ in range(max(1, args.warmup // 2)):
+        model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ho = model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = x_host.numel() * 4 + bbox_host.numel() * 4 + intr_host.numel() * 4
+    d2h = ho["joints_cam"].numel() * 4 + ho["joints_crop_img"].numel() * 4
+
+    # ---- per-launch timing of the dominant kernel: same steps again with CUDA events around every launch ----
+    model.profile(True)
+    for _ in range(args.steps):
+        model(x, bbox, cam)
+    csv = os.path.join(ROOT, "gpurun_out", "tc_launches.csv") if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+    tc_ms, tc_flops, tc_n = model.profile_read(csv)
+    model.profile(False)
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    if rank == 0:
+        peaks = load_peaks()
+        value = B * world * args.steps / (dev_ms * 1e-3)
+        achieved = tc_flops / (tc_ms * 1e-3) * 1e-12 if tc_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"HO3D_HandMvNet release config, synthetic 5-view B={B} per GPU, bf16, random-init weights",
+                       "views": views, "image": 256, "batch_per_gpu": B, "micro_batch": args.micro_batch,
+                       "parallelism": f"batch-sharded x{world} (replicated weights, NCCL all-gather of poses)",
+                       "l2": f"inputs {x.numel() * 4 / 2**20:.0f} MiB + {0.445 * B:.1f} GB of activations per step exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "api": "HandMvNet.forward_host -> hmv_forward_host (pinned host buffers; poses copied back)"},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
+                         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                         "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps,
+                         "kernel_share_of_step": (tc_ms / args.steps) / (dev_ms / args.steps),
+                         "timing": "second pass over the same steps with CUDA events around every launch",
+                         "end_to_end_model_tflops": FLOP_PER_SAMPLE_V5 * value / world * 1e-12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ps, ms, cores = cpu_oracle_throughput(1, 12, 3)
+            line["cpu_baseline"] = {"value": ps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "oracle/handmvnet_oracle.py forward, B=1 x 12 steps (+3 warm-up), fp32, all host threads",
+                                    "ms_per_forward": ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=16, help="samples per internal pass")
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

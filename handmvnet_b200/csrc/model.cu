@@ -123,8 +123,8 @@ struct hmv_handle {
     void *xpad = nullptr, *bufX = nullptr, *bufY = nullptr, *bufT1 = nullptr, *bufT2 = nullptr, *bufDS = nullptr;
     void* featbuf = nullptr;                      // where the backbone output lives (bufX or bufY)
     float *hm_int = nullptr, *xy = nullptr, *xy_scaled = nullptr, *wts = nullptr, *pe = nullptr, *basis = nullptr;
-    float *tokA_f32 = nullptr, *tokB_f32 = nullptr, *ybuf = nullptr, *hbuf = nullptr, *y2buf = nullptr;
-    void *tokA_lp = nullptr, *tokB_lp = nullptr, *qkvbuf = nullptr, *attbuf = nullptr, *hnbuf = nullptr, *f1buf = nullptr;
+    float *tok0_f32 = nullptr, *tokA_f32 = nullptr, *tokB_f32 = nullptr, *ybuf = nullptr, *hbuf = nullptr, *y2buf = nullptr;
+    void *tok0_lp = nullptr, *tokA_lp = nullptr, *tokB_lp = nullptr, *qkvbuf = nullptr, *attbuf = nullptr, *hnbuf = nullptr, *f1buf = nullptr;
     float* fused_f32 = nullptr;                   // final fusion output (one of tokA/tokB)
     float* joints_int = nullptr;
     float* gcn_w[3] = {nullptr, nullptr, nullptr};
@@ -138,6 +138,11 @@ struct hmv_handle {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     float *d_bbox = nullptr, *d_intr = nullptr, *d_hm = nullptr, *d_xy = nullptr, *d_j = nullptr;
     int host_cap = 0;
+    // optional per-launch profiling of the tensor-core GEMM kernel (bench.py roofline leg)
+    bool profiling = false;
+    struct ProfRec { int layer; int units; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace hmv {
@@ -323,7 +328,17 @@ static int run_layer(hmv_handle* h, Layer& L, int units, cudaStream_t s, void* o
         t.p.ep.M = M;
         if (out_override) t.p.ep.out = out_override;
         t.p.num_m_tiles = L.kind == LK_FLAT ? (M + 127) / 128 : units * t.p.tpi;
-        return tc_launch(t, h->num_sms, s);
+        if (!h->profiling) return tc_launch(t, h->num_sms, s);
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!h->ev_pool.empty()) { ev[i] = h->ev_pool.back(); h->ev_pool.pop_back(); }
+            else HMV_CUDA(cudaEventCreate(&ev[i]));
+        }
+        HMV_CUDA(cudaEventRecord(ev[0], s));
+        const int rc = tc_launch(t, h->num_sms, s);
+        HMV_CUDA(cudaEventRecord(ev[1], s));
+        h->prof.push_back({static_cast<int>(&L - h->layers.data()), units, ev[0], ev[1]});
+        return rc;
     }
     ConvF32Params p{};
     p.in = static_cast<const float*>(L.in);
@@ -531,10 +546,10 @@ static int build_heads(hmv_handle* h) {
     if (dev_alloc_t(h, &h->intr_int, static_cast<size_t>(h->mb_img) * 4 * 4)) return 1;
     if (dev_alloc_t(h, &h->joints_int, static_cast<size_t>(h->mb) * kJoints * 3 * 4)) return 1;
     const size_t tokb = static_cast<size_t>(rows_max) * h->pitch;
-    if (dev_alloc_t(h, &h->tokA_f32, tokb * 4) || dev_alloc_t(h, &h->tokB_f32, tokb * 4) || dev_alloc_t(h, &h->ybuf, tokb * 4) ||
+    if (dev_alloc_t(h, &h->tok0_f32, tokb * 4) || dev_alloc_t(h, &h->tokA_f32, tokb * 4) || dev_alloc_t(h, &h->tokB_f32, tokb * 4) || dev_alloc_t(h, &h->ybuf, tokb * 4) ||
         dev_alloc_t(h, &h->hbuf, tokb * 4) || dev_alloc_t(h, &h->y2buf, tokb * 4))
         return 1;
-    if (dev_alloc(h, &h->tokA_lp, tokb * e) || dev_alloc(h, &h->tokB_lp, tokb * e) || dev_alloc(h, &h->hnbuf, tokb * e) ||
+    if (dev_alloc(h, &h->tok0_lp, tokb * e) || dev_alloc(h, &h->tokA_lp, tokb * e) || dev_alloc(h, &h->tokB_lp, tokb * e) || dev_alloc(h, &h->hnbuf, tokb * e) ||
         dev_alloc(h, &h->qkvbuf, static_cast<size_t>(rows_max) * 3072 * e) ||
         dev_alloc(h, &h->attbuf, static_cast<size_t>(rows_max) * 1024 * e) ||
         dev_alloc(h, &h->f1buf, static_cast<size_t>(rows_max) * 128 * e))
@@ -622,8 +637,9 @@ static int build_heads(hmv_handle* h) {
     // ---- fusion transformer (fusion.py:7-30, layers.py:177-237) ----
     const int nl = h->cfg.fusion_layers;
     const int half = (nl - 1) / 2;
-    float* cur_f = h->tokA_f32; void* cur_l = h->tokA_lp;
-    float* nxt_f = h->tokB_f32; void* nxt_l = h->tokB_lp;
+    // tokens (+PE) stay in tok0 so the stage API can read them back; layers ping-pong between A and B
+    float* cur_f = h->tok0_f32; void* cur_l = h->tok0_lp;
+    float* nxt_f = h->tokA_f32; void* nxt_l = h->tokA_lp;
     int s_in = h->S;
     for (int i = 0; i < nl; ++i) {
         const std::string p = "joints_late_fusion.attn_fusion." + std::to_string(i);
@@ -658,8 +674,9 @@ static int build_heads(hmv_handle* h) {
         }
         fp.res_in = cur_f; fp.in_lp = cur_l; fp.out_f32 = nxt_f; fp.out_lp = nxt_l;
         h->fusion.push_back(fp);
-        float* tf = cur_f; cur_f = nxt_f; nxt_f = tf;
-        void* tl = cur_l; cur_l = nxt_l; nxt_l = tl;
+        cur_f = nxt_f; cur_l = nxt_l;
+        if (nxt_f == h->tokA_f32) { nxt_f = h->tokB_f32; nxt_l = h->tokB_lp; }
+        else { nxt_f = h->tokA_f32; nxt_l = h->tokA_lp; }
         s_in = fp.nq;
     }
     h->fused_f32 = cur_f;
@@ -717,7 +734,7 @@ static int run_sample_t(hmv_handle* h, int n_img, const float* bbox, const float
     TokenParams tp{};
     tp.g = static_cast<const float*>(h->bufDS); tp.ldg = 512; tp.wts = h->wts; tp.xy = h->xy;
     tp.bbox = bbox; tp.intr = intr; tp.pe = h->cfg.use_sin ? h->pe : nullptr;
-    tp.tok_f32 = h->tokA_f32; tp.tok_lp = h->tokA_lp;
+    tp.tok_f32 = h->tok0_f32; tp.tok_lp = h->tok0_lp;
     tp.n_img = n_img; tp.feat = h->feat; tp.d = h->d; tp.pitch = h->pitch; tp.tokens_per_sample = h->S;
     tp.use_pos2d = h->cfg.use_pos2d; tp.use_crop = h->cfg.use_crop;
     return tokens_launch<T>(tp, s);
@@ -836,6 +853,8 @@ int hmv_destroy(hmv_handle* h) {
     if (h->d_j) cudaFree(h->d_j);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
     delete h;
     return 0;
@@ -1001,7 +1020,7 @@ int hmv_tensor_get(hmv_handle* h, int32_t tensor, float* dst, int32_t batch, voi
             break;
         case HMV_T_TOKENS: {
             const size_t total = static_cast<size_t>(batch) * h->S * h->d;
-            hmv::rows_export_kernel<<<hmv::nblk(total), 256, 0, s>>>(h->tokA_f32, dst, h->d, h->pitch, total);
+            hmv::rows_export_kernel<<<hmv::nblk(total), 256, 0, s>>>(h->tok0_f32, dst, h->d, h->pitch, total);
             break;
         }
         case HMV_T_FUSED: {
@@ -1041,8 +1060,8 @@ int hmv_tensor_set(hmv_handle* h, int32_t tensor, const float* src, int32_t batc
             break;
         case HMV_T_TOKENS: {
             const size_t total = static_cast<size_t>(batch) * h->S * h->d;
-            if (h->bf16) hmv::rows_import_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(src, h->tokA_f32, static_cast<hmv::bf16*>(h->tokA_lp), h->d, h->pitch, total);
-            else hmv::rows_import_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(src, h->tokA_f32, static_cast<float*>(h->tokA_lp), h->d, h->pitch, total);
+            if (h->bf16) hmv::rows_import_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(src, h->tok0_f32, static_cast<hmv::bf16*>(h->tok0_lp), h->d, h->pitch, total);
+            else hmv::rows_import_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(src, h->tok0_f32, static_cast<float*>(h->tok0_lp), h->d, h->pitch, total);
             break;
         }
         case HMV_T_FUSED: {
@@ -1163,6 +1182,39 @@ int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const fl
     for (void* p : h->allocs) cudaFree(p);
     if (flag_host) cudaFreeHost(flag_host);
     return rc;
+}
+
+int hmv_profile_enable(hmv_handle* h, int32_t enable) {
+    HMV_CHECK(h, "null handle");
+    h->profiling = enable != 0;
+    return 0;
+}
+
+/* Sums the recorded tensor-core GEMM launches since the last read: device time (ms), algorithmic FLOPs
+ * (2*M*N*K over the real, unpadded extents) and launch count; optionally appends one CSV line per launch. */
+int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc_launches, const char* csv_path) {
+    HMV_CHECK(h, "null handle");
+    HMV_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0, fl = 0.0;
+    FILE* f = csv_path ? fopen(csv_path, "w") : nullptr;
+    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops\n");
+    for (auto& r : h->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        const hmv::Layer& L = h->layers[r.layer];
+        const double M = static_cast<double>(r.units) * L.rows_per_unit();
+        const double kreal = L.kind == hmv::LK_STEM ? 147.0 : (L.kind == hmv::LK_FLAT ? static_cast<double>(L.cin) : static_cast<double>(L.cin) * L.ksize * L.ksize);
+        const double flop = 2.0 * M * L.cout * kreal;
+        ms += t; fl += flop;
+        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f\n", L.name.c_str(), M, L.cout, kreal, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12);
+        h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
+    }
+    if (f) fclose(f);
+    if (tc_ms) *tc_ms = ms;
+    if (tc_flops) *tc_flops = fl;
+    if (tc_launches) *tc_launches = static_cast<int64_t>(h->prof.size());
+    h->prof.clear();
+    return 0;
 }
 
 int64_t hmv_launch_count(hmv_handle* h) { return h ? h->launches : 0; }

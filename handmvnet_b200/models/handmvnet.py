@@ -423,5 +423,15 @@ class HandMvNet(nn.Module):
         c, hh, ww = chw[0], chw[1], chw[2]
         return buf[: n_img * c * hh * ww].view(n_img, c, hh, ww)
 
+    def profile(self, enable: bool):
+        _lib.check(_lib.load().hmv_profile_enable(self._handle, int(enable)), "hmv_profile_enable")
+
+    def profile_read(self, csv_path=None):
+        """(device ms, algorithmic FLOPs, launches) of the tensor-core GEMM kernel since the last read."""
+        ms, fl, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+        _lib.check(_lib.load().hmv_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n),
+                                                csv_path.encode() if csv_path else None), "hmv_profile_read")
+        return ms.value, fl.value, n.value
+
     def launch_count(self):
         return int(_lib.load().hmv_launch_count(self._handle)) if self._handle is not None else 0

@@ -109,6 +109,13 @@ int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const fl
                     int32_t cout, int32_t ksize, int32_t stride, int32_t relu, float* elapsed_ms, int32_t iters,
                     void* stream);
 
+/* Measurement support (bench.py roofline leg): when enabled every launch of the tensor-core implicit-GEMM
+ * kernel is bracketed by CUDA events on its stream.  hmv_profile_read() synchronises, returns the summed device
+ * time, the algorithmic FLOPs (2*M*N*K over the real extents) and the launch count since the last read, and
+ * writes one CSV line per launch when csv_path is non-NULL. */
+int hmv_profile_enable(hmv_handle* h, int32_t enable);
+int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc_launches, const char* csv_path);
+
 /* Number of kernels enqueued by the handle so far (bench.py's gpu_launches claim). */
 int64_t hmv_launch_count(hmv_handle* h);
 int hmv_num_sms(hmv_handle* h);
