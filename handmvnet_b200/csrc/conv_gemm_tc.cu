@@ -112,6 +112,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// TMA store of a shared-memory box, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // epilogue: 16 consecutive output columns of one row
@@ -174,41 +203,56 @@ __device__ __forceinline__ void epilogue_16(const Epilogue& ep, float (&v)[16], 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+constexpr int kChunkCols = 64;                         // staged output chunk: 128 rows x 64 bf16 = 16 KiB
+constexpr int kChunkBytes = kTcBlockM * kChunkCols * 2;
+
+template <int BN, int MODE>
 struct TcCfg {
     static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;       // 16 KiB
     static constexpr int kBBytes = BN * kTcBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+    // staging ring for the TMA-store epilogues: 2 chunks for mainloop-bound layers, 4 for store-bound ones
+    static constexpr int kNumC = MODE == TC_DIRECT ? 0 : (MODE == TC_STORE ? 2 : 4);
+    static constexpr int kCBytes = kNumC * kChunkBytes;
+    static constexpr int kStagesRaw = (224 * 1024 - kCBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
+    static_assert(MODE == TC_DIRECT || BN % kChunkCols == 0, "TMA-store epilogue works on 64-column chunks");
+    static_assert(kSmemBytes <= 227 * 1024 && kStages >= 2, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ TcParams p) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, MODE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kCBytes);
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = full0 + 8 * Cfg::kStages;
     const uint32_t tfull0 = empty0 + 8 * Cfg::kStages;
     const uint32_t tempty0 = tfull0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    const uint32_t cfull0 = tempty0 + 16;                  // residual chunk landed (4 slots)
+    const uint32_t cempty0 = cfull0 + 32;                  // staging slot free again (4 slots)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 12);
     const uint32_t smem_base = smem_u32(smem);
+    const uint32_t cbuf0 = smem_base + Cfg::kStages * Cfg::kStageBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool has_res = MODE == TC_STORE_RES && p.ep.res_mode == RES_BF16;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (MODE != TC_DIRECT) prefetch_tmap(&tmC);
+        if (has_res) prefetch_tmap(&tmR);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
             mbar_init(empty0 + 8 * i, 1);
@@ -216,6 +260,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, 4);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(cfull0 + 8 * i, 1);
+            mbar_init(cempty0 + 8 * i, 4);
         }
         fence_barrier_init();
     }
@@ -234,7 +282,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int num_kb = p.num_taps * p.cblks;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (A / B operand tiles) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -295,41 +343,130 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
+    } else if (warp == 6) {
+        // ===================== residual producer (TC_STORE_RES with a bf16 residual) =====================
+        if (MODE == TC_STORE_RES && has_res && lane == 0) {
+            uint32_t g = 0;
+            bool alive = true;
+            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int m_tile = tile / p.num_n_tiles;
+                for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
+                    const uint32_t slot = g % Cfg::kNumC, use = g / Cfg::kNumC;
+                    if (!mbar_wait(cempty0 + 8 * slot, (use & 1) ^ 1, p.err_flag, 5)) { alive = false; break; }
+                    mbar_arrive_expect_tx(cfull0 + 8 * slot, kChunkBytes);
+                    tma_load_2d(cbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
+                                m_tile * kTcBlockM);
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
         bool alive = true;
+        uint32_t g = 0;                                    // running chunk counter (TMA-store modes)
         for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = tile / p.num_n_tiles;
             if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) { alive = false; break; }
             tc_fence_after();
-            const int row = m_tile * kTcBlockM + quarter * 32 + lane;
-            const bool row_ok = row < p.ep.M;
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            if constexpr (MODE == TC_DIRECT) {
+                const int row = m_tile * kTcBlockM + quarter * 32 + lane;
+                const bool row_ok = row < p.ep.M;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r0[16], r1[16];
-                tmem_ld16(t0 + c, r0);
-                if (c + 16 < BN) tmem_ld16(t0 + c + 16, r1);
-                tmem_ld_wait();
-                float v[16];
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(t0 + c, r0);
+                    if (c + 16 < BN) tmem_ld16(t0 + c + 16, r1);
+                    tmem_ld_wait();
+                    float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-                if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
-                if (c + 16 < BN) {
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
+                    if (c + 16 < BN) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
-                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                        if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            } else {
+                const int act = p.ep.act;
+#pragma unroll 1
+                for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
+                    const uint32_t slot = g % Cfg::kNumC, use = g / Cfg::kNumC;
+                    if (has_res) {
+                        if (!mbar_wait(cfull0 + 8 * slot, use & 1, p.err_flag, 6)) { alive = false; break; }
+                    } else {
+                        if (lane == 0) bulk_wait_read<Cfg::kNumC - 1>();     // my slab's previous store has left smem
+                        __syncwarp();
+                    }
+                    const uint32_t slab = cbuf0 + slot * kChunkBytes + quarter * (32 * 128);
+                    const uint32_t rowaddr = slab + lane * 128;
+                    const int col0 = n_tile * BN + c * kChunkCols;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t r[32];
+                        tmem_ld32(t0 + c * kChunkCols + hf * 32, r);
+                        tmem_ld_wait();
+                        if (c == BN / kChunkCols - 1 && hf == 1) {           // accumulator drained: hand TMEM back early
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                        // 4 x (8 columns = 16 bytes)
+                            float v[8];
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + hf * 32 + j * 8));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + hf * 32 + j * 8 + 4));
+                            v[0] = __uint_as_float(r[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[j * 8 + 1]) + b0.y;
+                            v[2] = __uint_as_float(r[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[j * 8 + 3]) + b0.w;
+                            v[4] = __uint_as_float(r[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[j * 8 + 5]) + b1.y;
+                            v[6] = __uint_as_float(r[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[j * 8 + 7]) + b1.w;
+                            const uint32_t a = rowaddr + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4);   // 128B swizzle
+                            if (has_res) {
+                                const uint4 q = lds128(a);
+                                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                                v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+                                v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+                            }
+                            if (act == ACT_RELU) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            } else if (act == ACT_GELU) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                            sts128(a, o);
+                        }
+                    }
+                    fence_async_smem();                    // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, slab, col0, m_tile * kTcBlockM + quarter * 32);
+                        bulk_commit();
+                        if (has_res && g > 0) {            // deferred release: chunk g-1's store has finished reading smem
+                            bulk_wait_read<1>();
+                            mbar_arrive(cempty0 + 8 * ((g - 1) % Cfg::kNumC));
+                        }
+                    }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if constexpr (MODE != TC_DIRECT) {
+            if (lane == 0) bulk_wait_read<0>();             // staged data must stay valid until every store has read it
+            __syncwarp();
         }
     }
 
@@ -351,10 +488,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-template <int BN>
+template <int BN, int MODE>
 static int set_attr() {
-    HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<BN>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<BN, MODE>::kSmemBytes));
     return 0;
 }
 
@@ -364,7 +501,10 @@ int tc_init() {
     cudaDriverEntryPointQueryResult qres;
     HMV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     HMV_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    if (set_attr<32>() || set_attr<64>() || set_attr<128>() || set_attr<176>() || set_attr<256>()) return 1;
+    if (set_attr<32, TC_DIRECT>() || set_attr<64, TC_DIRECT>() || set_attr<128, TC_DIRECT>() || set_attr<176, TC_DIRECT>() ||
+        set_attr<256, TC_DIRECT>() || set_attr<64, TC_STORE>() || set_attr<128, TC_STORE>() || set_attr<256, TC_STORE>() ||
+        set_attr<64, TC_STORE_RES>() || set_attr<128, TC_STORE_RES>() || set_attr<256, TC_STORE_RES>())
+        return 1;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -405,6 +545,13 @@ int tc_make_tmap_wgt(CUtensorMap* out, const void* base, uint64_t k_total, uint6
     return encode(out, base, 2, dims, strides, box);
 }
 
+int tc_make_tmap_out(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, int box_rows) {
+    const uint64_t dims[2] = {cols, rows};
+    const uint64_t strides[1] = {cols * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kChunkCols), static_cast<uint32_t>(box_rows)};
+    return encode(out, base, 2, dims, strides, box);
+}
+
 int tc_pick_bn(int n) {
     if (n <= 32) return 32;
     if (n <= 64) return 64;
@@ -415,23 +562,36 @@ int tc_pick_bn(int n) {
     return 0;
 }
 
-template <int BN>
+template <int BN, int MODE>
 static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    conv_gemm_tc_kernel<BN><<<grid, kTcThreads, TcCfg<BN>::kSmemBytes, stream>>>(l.tmA, l.tmB, l.p);
+    conv_gemm_tc_kernel<BN, MODE><<<grid, kTcThreads, TcCfg<BN, MODE>::kSmemBytes, stream>>>(l.tmA, l.tmB, l.tmC, l.tmR, l.p);
     HMV_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int BN>
+static int launch_mode(const TcLaunch& l, int num_sms, cudaStream_t stream) {
+    if constexpr (BN % kChunkCols == 0) {
+        if (l.mode == TC_STORE) return launch_bn<BN, TC_STORE>(l, num_sms, stream);
+        if (l.mode == TC_STORE_RES) return launch_bn<BN, TC_STORE_RES>(l, num_sms, stream);
+    }
+    if (l.mode != TC_DIRECT) {
+        set_error("tc_launch: TMA-store epilogue needs a tile width that is a multiple of 64");
+        return 1;
+    }
+    return launch_bn<BN, TC_DIRECT>(l, num_sms, stream);
 }
 
 int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0 || l.p.num_n_tiles <= 0) return 0;
     switch (l.bn) {
-        case 32: return launch_bn<32>(l, num_sms, stream);
-        case 64: return launch_bn<64>(l, num_sms, stream);
-        case 128: return launch_bn<128>(l, num_sms, stream);
-        case 176: return launch_bn<176>(l, num_sms, stream);
-        case 256: return launch_bn<256>(l, num_sms, stream);
+        case 32: return launch_mode<32>(l, num_sms, stream);
+        case 64: return launch_mode<64>(l, num_sms, stream);
+        case 128: return launch_mode<128>(l, num_sms, stream);
+        case 176: return launch_mode<176>(l, num_sms, stream);
+        case 256: return launch_mode<256>(l, num_sms, stream);
     }
     set_error("tc_launch: unsupported BN " + std::to_string(l.bn));
     return 1;

@@ -24,7 +24,7 @@ namespace hmv {
 constexpr int kTcBlockM = 128;
 constexpr int kTcBlockK = 64;          // bf16 elements -> 128 B = one swizzle-128B row
 constexpr int kTcUmmaK = 16;
-constexpr int kTcThreads = 192;        // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kTcThreads = 224;        // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue, warp6 residual TMA
 constexpr int kTcMaxTaps = 9;
 
 struct TcTap { int c_off, dw, a, dh; };
@@ -39,10 +39,18 @@ struct TcParams {
     int* err_flag;                     // set to non-zero on an mbarrier timeout
 };
 
+// Epilogue variants.  DIRECT: registers -> global (fp32 / NCHW / remapped-residual outputs).
+// STORE / STORE_RES: bf16 NHWC outputs staged through 128B-swizzled shared memory and written with TMA
+// stores (64-column x 32-row slabs per epilogue warp); STORE_RES additionally prefetches the bf16 residual
+// tile with TMA (a dedicated producer warp) and has a deeper staging ring for the store-bound 1x1 layers.
+enum TcMode { TC_DIRECT = 0, TC_STORE = 1, TC_STORE_RES = 2 };
+
 struct TcLaunch {                      // everything needed to enqueue one layer
     CUtensorMap tmA, tmB;
+    CUtensorMap tmC, tmR;              // output / residual maps (TC_STORE* only)
     TcParams p;
     int bn;
+    int mode;
 };
 
 // Host API -------------------------------------------------------------------------------------
@@ -50,6 +58,8 @@ int tc_init();                                               // resolves cuTenso
 int tc_make_tmap_act(CUtensorMap* out, const void* base, const uint64_t dims[5],
                      const uint64_t strides_bytes[4], const uint32_t box[5]);
 int tc_make_tmap_wgt(CUtensorMap* out, const void* base, uint64_t k_total, uint64_t n_alloc, int bn);
+// [rows, cols] bf16 row-major tensor, box = 64 columns x box_rows rows (output slabs: 32, residual tiles: 128)
+int tc_make_tmap_out(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, int box_rows);
 int tc_pick_bn(int n);                                       // tile width for a given output width
 int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream);
 

@@ -456,52 +456,95 @@ template int layernorm_launch<float>(const float*, int, const float*, const floa
                                      const float*, float*, int, int, int, float, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
-// Chebyshev graph-conv head (reference nets.py:133-139, layers.py:387-403): one CTA per sample.
-// Layer: out = sum_k T_k (X W_k) + b ; thread c owns output column c, so T_k is applied in registers.
+// Chebyshev graph-conv head (reference nets.py:133-139, layers.py:387-403), fp32.
+// Layer: out = sum_k T_k (X W_k) + b.  A CTA owns 64 output columns; its 256 threads are 64 columns x 4 K-splits,
+// weights stream from L2 in double-buffered batches of 8 (the loop is L2-latency bound otherwise), partial
+// products are reduced through shared memory and T_k is applied per column in registers.
+//   gcn_l1_kernel : grid (batch, 256/64)   X[21, d_in] -> H1[21, 256]          (95 % of the head's FLOPs)
+//   gcn_l23_kernel: grid (batch)           H1 -> H2[21, 64] -> joints[21, 3]
 // ------------------------------------------------------------------------------------------------
 constexpr int kGcnPad = 24;                    // 21 joints padded to 6 float4
+constexpr int kGcnCols = 64;                   // output columns per CTA
+constexpr int kGcnSplit = 4;                   // K-splits
 
-__device__ __forceinline__ void gcn_layer(const float* __restrict__ xt /*[cin][24] smem*/, int cin,
-                                          const float* __restrict__ w /*[3][cin][cout]*/, const float* __restrict__ bias,
-                                          int cout, const float* __restrict__ basis /*[3][21][21] smem*/, bool leaky,
-                                          float (&o)[kJoints], int c) {
+// Computes, for column `col` (global) and K-split `ks`, the partial z_k[s] = sum_{i in split} X[s, i] W_k[i, col],
+// reduces over the splits through `red` and returns (in threads with ks == 0) o[r] = bias + sum_k (T_k z_k)[r].
+__device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[cin][24] smem*/, int cin,
+                                                const float* __restrict__ w /*[3][cin][cout]*/,
+                                                const float* __restrict__ bias, int cout, int col, int lcol, int ks,
+                                                const float* __restrict__ basis /*[3][21][21] smem*/,
+                                                float* __restrict__ red /*[kGcnSplit][24][kGcnCols] smem*/, bool leaky,
+                                                float (&o)[kJoints], bool active) {
+    const int per = cin / kGcnSplit, i_lo = ks * per;
+    if (ks == 0 && active) {
 #pragma unroll
-    for (int r = 0; r < kJoints; ++r) o[r] = bias[c];
+        for (int r = 0; r < kJoints; ++r) o[r] = bias[col];
+    }
     for (int k = 0; k < 3; ++k) {
         float z[kGcnPad];
 #pragma unroll
         for (int r = 0; r < kGcnPad; ++r) z[r] = 0.f;
-        const float* wk = w + static_cast<size_t>(k) * cin * cout + c;
-        for (int i = 0; i < cin; ++i) {
-            const float wv = __ldg(wk + static_cast<size_t>(i) * cout);
-            const float4* xr = reinterpret_cast<const float4*>(xt + i * kGcnPad);
+        if (active) {
+            const float* wk = w + (static_cast<size_t>(k) * cin + i_lo) * cout + col;
+            float wc[8], wn[8];
 #pragma unroll
-            for (int q = 0; q < kGcnPad / 4; ++q) {
-                const float4 xv = xr[q];
-                z[4 * q] = fmaf(xv.x, wv, z[4 * q]);         z[4 * q + 1] = fmaf(xv.y, wv, z[4 * q + 1]);
-                z[4 * q + 2] = fmaf(xv.z, wv, z[4 * q + 2]); z[4 * q + 3] = fmaf(xv.w, wv, z[4 * q + 3]);
+            for (int u = 0; u < 8; ++u) wc[u] = u < per ? __ldg(wk + static_cast<size_t>(u) * cout) : 0.f;
+            for (int i0 = 0; i0 < per; i0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) wn[u] = (i0 + 8 + u) < per ? __ldg(wk + static_cast<size_t>(i0 + 8 + u) * cout) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (i0 + u < per) {
+                        const float4* xr = reinterpret_cast<const float4*>(xt + (i_lo + i0 + u) * kGcnPad);
+                        const float wv = wc[u];
+#pragma unroll
+                        for (int q = 0; q < kGcnPad / 4; ++q) {
+                            const float4 xv = xr[q];
+                            z[4 * q] = fmaf(xv.x, wv, z[4 * q]);         z[4 * q + 1] = fmaf(xv.y, wv, z[4 * q + 1]);
+                            z[4 * q + 2] = fmaf(xv.z, wv, z[4 * q + 2]); z[4 * q + 3] = fmaf(xv.w, wv, z[4 * q + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) wc[u] = wn[u];
             }
         }
-        const float* tk = basis + k * kJoints * kJoints;
+        __syncthreads();                       // previous use of `red` is over
+        if (active) {
 #pragma unroll
-        for (int r = 0; r < kJoints; ++r) {
-            float a = 0.f;
+            for (int r = 0; r < kJoints; ++r) red[(ks * kGcnPad + r) * kGcnCols + lcol] = z[r];
+        }
+        __syncthreads();
+        if (ks == 0 && active) {
 #pragma unroll
-            for (int s = 0; s < kJoints; ++s) a = fmaf(tk[r * kJoints + s], z[s], a);
-            o[r] += a;
+            for (int r = 0; r < kJoints; ++r) {
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < kGcnSplit; ++q) a += red[(q * kGcnPad + r) * kGcnCols + lcol];
+                z[r] = a;
+            }
+            const float* tk = basis + k * kJoints * kJoints;
+#pragma unroll
+            for (int r = 0; r < kJoints; ++r) {
+                float a = 0.f;
+#pragma unroll
+                for (int s2 = 0; s2 < kJoints; ++s2) a = fmaf(tk[r * kJoints + s2], z[s2], a);
+                o[r] += a;
+            }
         }
     }
-    if (leaky) {
+    if (leaky && ks == 0 && active) {
 #pragma unroll
         for (int r = 0; r < kJoints; ++r) o[r] = o[r] > 0.f ? o[r] : 0.01f * o[r];
     }
 }
 
 __global__ void __launch_bounds__(256)
-gcn_kernel(const GcnParams p) {
+gcn_l1_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
     extern __shared__ __align__(16) float gsm[];
-    float* xt = gsm;                                   // [max(d_in,256)][24]
-    float* basis = gsm + static_cast<size_t>(p.d_in > 256 ? p.d_in : 256) * kGcnPad;
+    float* xt = gsm;                                       // [d_in][24]
+    float* basis = xt + static_cast<size_t>(p.d_in) * kGcnPad;
+    float* red = basis + 3 * kJoints * kJoints + 1;        // keep 16B alignment irrelevant: scalar access
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* x = p.x + static_cast<size_t>(b) * kJoints * p.ld;
     for (int i = tid; i < p.d_in * kGcnPad; i += blockDim.x) {
@@ -510,38 +553,62 @@ gcn_kernel(const GcnParams p) {
     }
     for (int i = tid; i < 3 * kJoints * kJoints; i += blockDim.x) basis[i] = p.basis[i];
     __syncthreads();
+    const int lcol = tid % kGcnCols, ks = tid / kGcnCols;
+    const int col = blockIdx.y * kGcnCols + lcol;
     float o[kJoints];
-    gcn_layer(xt, p.d_in, p.w[0], p.b[0], 256, basis, true, o, tid);           // 256 threads <-> 256 columns
-    __syncthreads();
+    gcn_layer_split(xt, p.d_in, p.w[0], p.b[0], 256, col, lcol, ks, basis, red, true, o, true);
+    if (ks == 0) {
 #pragma unroll
-    for (int r = 0; r < kJoints; ++r) xt[tid * kGcnPad + r] = o[r];
-    xt[tid * kGcnPad + 21] = 0.f; xt[tid * kGcnPad + 22] = 0.f; xt[tid * kGcnPad + 23] = 0.f;
-    __syncthreads();
-    if (tid < 64) gcn_layer(xt, 256, p.w[1], p.b[1], 64, basis, true, o, tid);
-    __syncthreads();
-    if (tid < 64) {
-#pragma unroll
-        for (int r = 0; r < kJoints; ++r) xt[tid * kGcnPad + r] = o[r];
-        xt[tid * kGcnPad + 21] = 0.f; xt[tid * kGcnPad + 22] = 0.f; xt[tid * kGcnPad + 23] = 0.f;
-    }
-    __syncthreads();
-    if (tid < 3) {
-        gcn_layer(xt, 64, p.w[2], p.b[2], 3, basis, false, o, tid);
-#pragma unroll
-        for (int r = 0; r < kJoints; ++r) p.out[(static_cast<size_t>(b) * kJoints + r) * 3 + tid] = o[r];
+        for (int r = 0; r < kJoints; ++r) h1[(static_cast<size_t>(b) * kJoints + r) * 256 + col] = o[r];
     }
 }
 
-int gcn_launch(const GcnParams& p, cudaStream_t s) {
+__global__ void __launch_bounds__(256)
+gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
+    extern __shared__ __align__(16) float gsm[];
+    float* xt = gsm;                                       // [256][24]
+    float* basis = xt + 256 * kGcnPad;
+    float* red = basis + 3 * kJoints * kJoints + 1;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* x = h1 + static_cast<size_t>(b) * kJoints * 256;
+    for (int i = tid; i < 256 * kGcnPad; i += blockDim.x) {
+        const int c = i / kGcnPad, r = i % kGcnPad;
+        xt[i] = r < kJoints ? x[r * 256 + c] : 0.f;
+    }
+    for (int i = tid; i < 3 * kJoints * kJoints; i += blockDim.x) basis[i] = p.basis[i];
+    __syncthreads();
+    const int lcol = tid % kGcnCols, ks = tid / kGcnCols;
+    float o[kJoints];
+    gcn_layer_split(xt, 256, p.w[1], p.b[1], 64, lcol, lcol, ks, basis, red, true, o, true);
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) xt[lcol * kGcnPad + r] = o[r];
+        xt[lcol * kGcnPad + 21] = 0.f; xt[lcol * kGcnPad + 22] = 0.f; xt[lcol * kGcnPad + 23] = 0.f;
+    }
+    __syncthreads();
+    const bool active = lcol < 3;
+    gcn_layer_split(xt, 64, p.w[2], p.b[2], 3, lcol, lcol, ks, basis, red, false, o, active);
+    if (ks == 0 && active) {
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) p.out[(static_cast<size_t>(b) * kJoints + r) * 3 + lcol] = o[r];
+    }
+}
+
+int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
     if (p.batch == 0) return 0;
-    HMV_CHECK(p.d_in <= 1024, "gcn: d_in too large");
-    const size_t smem = (static_cast<size_t>(p.d_in > 256 ? p.d_in : 256) * kGcnPad + 3 * kJoints * kJoints) * sizeof(float);
+    HMV_CHECK(p.d_in <= 1024 && p.d_in % kGcnSplit == 0, "gcn: d_in must be a multiple of 4 and <= 1024");
+    const size_t smem = (static_cast<size_t>(p.d_in) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
+    const size_t smem2 = (static_cast<size_t>(256) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
-        HMV_CUDA(cudaFuncSetAttribute(gcn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
         configured = smem;
     }
-    gcn_kernel<<<p.batch, 256, smem, s>>>(p);
+    gcn_l1_kernel<<<dim3(p.batch, 256 / kGcnCols), 256, smem, s>>>(p, h1_scratch);
+    HMV_CUDA(cudaGetLastError());
+    gcn_l23_kernel<<<p.batch, 256, smem2, s>>>(p, h1_scratch);
     HMV_CUDA(cudaGetLastError());
     return 0;
 }

@@ -70,6 +70,7 @@ struct GcnParams {
     float* out;            // [batch, 21, 3]
     int batch;
 };
-int gcn_launch(const GcnParams& p, cudaStream_t s);
+// h1_scratch: [batch, 21, 256] fp32 workspace for the first layer's output
+int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s);
 
 }  // namespace hmv

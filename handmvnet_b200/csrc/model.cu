@@ -127,6 +127,7 @@ struct hmv_handle {
     void *tok0_lp = nullptr, *tokA_lp = nullptr, *tokB_lp = nullptr, *qkvbuf = nullptr, *attbuf = nullptr, *hnbuf = nullptr, *f1buf = nullptr;
     float* fused_f32 = nullptr;                   // final fusion output (one of tokA/tokB)
     float* joints_int = nullptr;
+    float* gcn_h1 = nullptr;
     float* gcn_w[3] = {nullptr, nullptr, nullptr};
     float* gcn_b[3] = {nullptr, nullptr, nullptr};
     float *bbox_int = nullptr, *intr_int = nullptr;
@@ -312,6 +313,25 @@ static int build_tc(hmv_handle* h, Layer& L) {
     if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
         return 1;
+    }
+    // epilogue variant: bf16 NHWC outputs go through shared memory + TMA stores (see conv_gemm_tc.cuh)
+    t.mode = TC_DIRECT;
+    t.tmC = t.tmA; t.tmR = t.tmA;      // valid placeholders (never dereferenced in TC_DIRECT)
+    const bool identity_res = L.ep.res_mode == RES_NONE || (L.ep.res_mode == RES_BF16 && L.ep.res_group >= (1 << 30));
+    if (L.ep.out_mode == OUT_BF16_ROWMAJOR && L.bn % 64 == 0 && identity_res && L.ep.ldc % 8 == 0) {
+        const uint64_t rows = N * L.rows_per_unit();
+        t.mode = L.ep.res_mode == RES_BF16 ? TC_STORE_RES : (L.K >= 512 ? TC_STORE : TC_STORE_RES);
+        if (tc_make_tmap_out(&t.tmC, L.ep.out, L.ep.ldc, rows, 32)) {
+            set_error(std::string(get_error()) + " [C map of " + L.name + "]");
+            return 1;
+        }
+        if (L.ep.res_mode == RES_BF16) {
+            HMV_CHECK(L.ep.res_ld % 8 == 0, "residual pitch must be a multiple of 8 in " + L.name);
+            if (tc_make_tmap_out(&t.tmR, L.ep.residual, L.ep.res_ld, rows, 128)) {
+                set_error(std::string(get_error()) + " [R map of " + L.name + "]");
+                return 1;
+            }
+        }
     }
     return 0;
 }
@@ -545,6 +565,7 @@ static int build_heads(hmv_handle* h) {
     if (dev_alloc_t(h, &h->bbox_int, static_cast<size_t>(h->mb_img) * 4 * 4)) return 1;
     if (dev_alloc_t(h, &h->intr_int, static_cast<size_t>(h->mb_img) * 4 * 4)) return 1;
     if (dev_alloc_t(h, &h->joints_int, static_cast<size_t>(h->mb) * kJoints * 3 * 4)) return 1;
+    if (dev_alloc_t(h, &h->gcn_h1, static_cast<size_t>(h->mb) * kJoints * 256 * 4)) return 1;
     const size_t tokb = static_cast<size_t>(rows_max) * h->pitch;
     if (dev_alloc_t(h, &h->tok0_f32, tokb * 4) || dev_alloc_t(h, &h->tokA_f32, tokb * 4) || dev_alloc_t(h, &h->tokB_f32, tokb * 4) || dev_alloc_t(h, &h->ybuf, tokb * 4) ||
         dev_alloc_t(h, &h->hbuf, tokb * 4) || dev_alloc_t(h, &h->y2buf, tokb * 4))
@@ -764,8 +785,8 @@ static int run_gcn(hmv_handle* h, int n, float* out, cudaStream_t s) {
     g.x = h->fused_f32; g.ld = h->pitch; g.d_in = h->d;
     for (int i = 0; i < 3; ++i) { g.w[i] = h->gcn_w[i]; g.b[i] = h->gcn_b[i]; }
     g.basis = h->basis; g.out = out ? out : h->joints_int; g.batch = n;
-    ++h->launches;
-    return gcn_launch(g, s);
+    h->launches += 2;
+    return gcn_launch(g, h->gcn_h1, s);
 }
 
 // one micro-batch of n <= mb samples, all pointers already offset

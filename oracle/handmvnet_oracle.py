@@ -154,12 +154,12 @@ def make_state_dict(cfg: dict, seed: int = 0, randomize_norm: bool = True) -> "O
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / (fan_in + fan_out))
         elif kind == "cheb_bias":
             t = torch.randn(shape, generator=g) * 1e-3 if randomize_norm else torch.zeros(shape)
-        elif kind in ("bn_gamma", "ln_gamma"):
-            t = torch.rand(shape, generator=g) + 0.5 if randomize_norm else torch.ones(shape)
+        elif kind in ("bn_gamma", "ln_gamma"):        # U(0.75, 1.25): visible in a wrong fold, yet well conditioned
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75 if randomize_norm else torch.ones(shape)
         elif kind in ("bn_beta", "ln_beta", "bn_mean"):
             t = torch.randn(shape, generator=g) * 0.1 if randomize_norm else torch.zeros(shape)
         elif kind == "bn_var":
-            t = torch.rand(shape, generator=g) + 0.5 if randomize_norm else torch.ones(shape)
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75 if randomize_norm else torch.ones(shape)
         elif kind == "count":
             t = torch.zeros((), dtype=torch.int64)
         else:  # pragma: no cover
