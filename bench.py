@@ -46,7 +46,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -75,7 +75,11 @@ class ClockSampler:
                 continue
             mx = max(mx, cmax)
             power = max(power, pw)
-            if pw > 250:                       # under load
+            try:
+                util = float(r[8])
+            except (ValueError, IndexError):
+                util = 0.0
+            if pw > 250 or util >= 50:         # under load
                 sm.append(clk)
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if val.lower().startswith("active"):
@@ -168,12 +172,12 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     launches0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -184,7 +188,6 @@ def run_own(args):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = model.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     assert torch.isfinite(out["joints_cam"]).all()
 
     # ---- end to end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
@@ -208,6 +211,7 @@ def run_own(args):
     csv = os.path.join(ROOT, "gpurun_out", "tc_launches.csv") if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     tc_ms, tc_flops, tc_n = model.profile_read(csv)
     model.profile(False)
+    clocks = sampler.stop() if rank == 0 else None      # samples cover warm-up, timed, e2e and profiling passes
 
     times = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:

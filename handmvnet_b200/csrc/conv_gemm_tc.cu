@@ -211,9 +211,10 @@ struct TcCfg {
     static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;       // 16 KiB
     static constexpr int kBBytes = BN * kTcBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // staging ring for the TMA-store epilogues: 2 chunks for mainloop-bound layers, 4 for store-bound ones
-    static constexpr int kNumC = MODE == TC_DIRECT ? 0 : (MODE == TC_STORE ? 2 : 4);
-    static constexpr int kCBytes = kNumC * kChunkBytes;
+    // staging rings of the TMA-store epilogues (see TcMode)
+    static constexpr int kNumS = MODE == TC_DIRECT ? 0 : (MODE == TC_STORE_DEEP ? 4 : 2);     // store slots
+    static constexpr int kNumR = MODE == TC_STORE_RES ? 3 : 0;                                 // residual slots
+    static constexpr int kCBytes = (kNumS + kNumR) * kChunkBytes;
     static constexpr int kStagesRaw = (224 * 1024 - kCBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -242,7 +243,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t cempty0 = cfull0 + 32;                  // staging slot free again (4 slots)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 12);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t cbuf0 = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    const uint32_t sbuf0 = smem_base + Cfg::kStages * Cfg::kStageBytes;      // store staging ring
+    const uint32_t rbuf0 = sbuf0 + Cfg::kNumS * kChunkBytes;                  // residual ring
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -352,10 +354,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int n_tile = tile % p.num_n_tiles;
                 const int m_tile = tile / p.num_n_tiles;
                 for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
-                    const uint32_t slot = g % Cfg::kNumC, use = g / Cfg::kNumC;
+                    constexpr uint32_t R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
+                    const uint32_t slot = g % R, use = g / R;
                     if (!mbar_wait(cempty0 + 8 * slot, (use & 1) ^ 1, p.err_flag, 5)) { alive = false; break; }
                     mbar_arrive_expect_tx(cfull0 + 8 * slot, kChunkBytes);
-                    tma_load_2d(cbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
+                    tma_load_2d(rbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
                                 m_tile * kTcBlockM);
                 }
             }
@@ -400,15 +403,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int act = p.ep.act;
 #pragma unroll 1
                 for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
-                    const uint32_t slot = g % Cfg::kNumC, use = g / Cfg::kNumC;
+                    constexpr uint32_t S = Cfg::kNumS > 0 ? Cfg::kNumS : 1, R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
+                    const uint32_t sslot = g % S, rslot = g % R;
+                    if (lane == 0) bulk_wait_read<(Cfg::kNumS > 0 ? Cfg::kNumS - 1 : 0)>();   // my slab's previous store left smem
+                    __syncwarp();
                     if (has_res) {
-                        if (!mbar_wait(cfull0 + 8 * slot, use & 1, p.err_flag, 6)) { alive = false; break; }
-                    } else {
-                        if (lane == 0) bulk_wait_read<Cfg::kNumC - 1>();     // my slab's previous store has left smem
-                        __syncwarp();
+                        if (!mbar_wait(cfull0 + 8 * rslot, (g / R) & 1, p.err_flag, 6)) { alive = false; break; }
                     }
-                    const uint32_t slab = cbuf0 + slot * kChunkBytes + quarter * (32 * 128);
+                    const uint32_t slab = sbuf0 + sslot * kChunkBytes + quarter * (32 * 128);
                     const uint32_t rowaddr = slab + lane * 128;
+                    const uint32_t resaddr = rbuf0 + rslot * kChunkBytes + quarter * (32 * 128) + lane * 128;
                     const int col0 = n_tile * BN + c * kChunkCols;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -429,9 +433,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             v[2] = __uint_as_float(r[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[j * 8 + 3]) + b0.w;
                             v[4] = __uint_as_float(r[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[j * 8 + 5]) + b1.y;
                             v[6] = __uint_as_float(r[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[j * 8 + 7]) + b1.w;
-                            const uint32_t a = rowaddr + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4);   // 128B swizzle
+                            const uint32_t sw = (static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4;              // 128B swizzle
+                            const uint32_t a = rowaddr + sw;
                             if (has_res) {
-                                const uint4 q = lds128(a);
+                                const uint4 q = lds128(resaddr + sw);
                                 const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
                                 v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
                                 v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
@@ -452,12 +457,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     fence_async_smem();                    // generic-proxy smem writes -> visible to the TMA engine
                     __syncwarp();
                     if (lane == 0) {
+                        if (has_res) mbar_arrive(cempty0 + 8 * rslot);        // residual slot consumed by this warp
                         tma_store_2d(&tmC, slab, col0, m_tile * kTcBlockM + quarter * 32);
                         bulk_commit();
-                        if (has_res && g > 0) {            // deferred release: chunk g-1's store has finished reading smem
-                            bulk_wait_read<1>();
-                            mbar_arrive(cempty0 + 8 * ((g - 1) % Cfg::kNumC));
-                        }
                     }
                 }
             }
@@ -503,6 +505,7 @@ int tc_init() {
     HMV_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
     if (set_attr<32, TC_DIRECT>() || set_attr<64, TC_DIRECT>() || set_attr<128, TC_DIRECT>() || set_attr<176, TC_DIRECT>() ||
         set_attr<256, TC_DIRECT>() || set_attr<64, TC_STORE>() || set_attr<128, TC_STORE>() || set_attr<256, TC_STORE>() ||
+        set_attr<64, TC_STORE_DEEP>() || set_attr<128, TC_STORE_DEEP>() || set_attr<256, TC_STORE_DEEP>() ||
         set_attr<64, TC_STORE_RES>() || set_attr<128, TC_STORE_RES>() || set_attr<256, TC_STORE_RES>())
         return 1;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
@@ -575,6 +578,7 @@ template <int BN>
 static int launch_mode(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     if constexpr (BN % kChunkCols == 0) {
         if (l.mode == TC_STORE) return launch_bn<BN, TC_STORE>(l, num_sms, stream);
+        if (l.mode == TC_STORE_DEEP) return launch_bn<BN, TC_STORE_DEEP>(l, num_sms, stream);
         if (l.mode == TC_STORE_RES) return launch_bn<BN, TC_STORE_RES>(l, num_sms, stream);
     }
     if (l.mode != TC_DIRECT) {

@@ -40,10 +40,11 @@ struct TcParams {
 };
 
 // Epilogue variants.  DIRECT: registers -> global (fp32 / NCHW / remapped-residual outputs).
-// STORE / STORE_RES: bf16 NHWC outputs staged through 128B-swizzled shared memory and written with TMA
-// stores (64-column x 32-row slabs per epilogue warp); STORE_RES additionally prefetches the bf16 residual
-// tile with TMA (a dedicated producer warp) and has a deeper staging ring for the store-bound 1x1 layers.
-enum TcMode { TC_DIRECT = 0, TC_STORE = 1, TC_STORE_RES = 2 };
+// STORE*: bf16 NHWC outputs staged through 128B-swizzled shared memory and written with TMA stores
+// (64-column x 32-row slabs per epilogue warp).  STORE = 2 staging slots (mainloop-bound layers, keeps 4
+// operand stages at BN=256); STORE_DEEP = 4 slots (store-bound small-K layers); STORE_RES = 2 store slots plus
+// a separate 3-slot ring into which a dedicated producer warp prefetches the bf16 residual tile with TMA.
+enum TcMode { TC_DIRECT = 0, TC_STORE = 1, TC_STORE_DEEP = 2, TC_STORE_RES = 3 };
 
 struct TcLaunch {                      // everything needed to enqueue one layer
     CUtensorMap tmA, tmB;

@@ -475,7 +475,8 @@ __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[
                                                 const float* __restrict__ basis /*[3][21][21] smem*/,
                                                 float* __restrict__ red /*[kGcnSplit][24][kGcnCols] smem*/, bool leaky,
                                                 float (&o)[kJoints], bool active) {
-    const int per = cin / kGcnSplit, i_lo = ks * per;
+    const int per_max = (cin + kGcnSplit - 1) / kGcnSplit, i_lo = ks * per_max;
+    const int per = i_lo >= cin ? 0 : (cin - i_lo < per_max ? cin - i_lo : per_max);
     if (ks == 0 && active) {
 #pragma unroll
         for (int r = 0; r < kJoints; ++r) o[r] = bias[col];
@@ -597,7 +598,7 @@ gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
 
 int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
     if (p.batch == 0) return 0;
-    HMV_CHECK(p.d_in <= 1024 && p.d_in % kGcnSplit == 0, "gcn: d_in must be a multiple of 4 and <= 1024");
+    HMV_CHECK(p.d_in <= 1024, "gcn: d_in must be <= 1024");
     const size_t smem = (static_cast<size_t>(p.d_in) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
     const size_t smem2 = (static_cast<size_t>(256) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
     static size_t configured = 0;

@@ -320,7 +320,7 @@ static int build_tc(hmv_handle* h, Layer& L) {
     const bool identity_res = L.ep.res_mode == RES_NONE || (L.ep.res_mode == RES_BF16 && L.ep.res_group >= (1 << 30));
     if (L.ep.out_mode == OUT_BF16_ROWMAJOR && L.bn % 64 == 0 && identity_res && L.ep.ldc % 8 == 0) {
         const uint64_t rows = N * L.rows_per_unit();
-        t.mode = L.ep.res_mode == RES_BF16 ? TC_STORE_RES : (L.K >= 512 ? TC_STORE : TC_STORE_RES);
+        t.mode = L.ep.res_mode == RES_BF16 ? TC_STORE_RES : (L.K >= 512 ? TC_STORE : TC_STORE_DEEP);
         if (tc_make_tmap_out(&t.tmC, L.ep.out, L.ep.ldc, rows, 32)) {
             set_error(std::string(get_error()) + " [C map of " + L.name + "]");
             return 1;

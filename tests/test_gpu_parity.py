@@ -80,9 +80,9 @@ def _forward(m, x, bbox, intr, crop=True):
     return {k: v.cpu() for k, v in out.items()}
 
 
-def _well_conditioned(heatmap, temperature=1000.0, margin=0.02):
+def _well_conditioned(heatmap, temperature=1000.0, margin=5e-3):
     """Joints whose soft-argmax is insensitive to fp32 noise: the runner-up pixel is at least `margin` below the
-    maximum (exp(-1000*0.02) = 2e-9).  Near ties make soft_argmax_2d(T=1000) discontinuous."""
+    maximum (exp(-1000*0.005) = 7e-3 of the weight, moved by <1 % under 1e-5 heat-map noise).  Near ties make soft_argmax_2d(T=1000) discontinuous."""
     flat = heatmap.flatten(-2)
     top2 = flat.topk(2, dim=-1).values
     return (top2[..., 0] - top2[..., 1]) > margin
@@ -90,28 +90,33 @@ def _well_conditioned(heatmap, temperature=1000.0, margin=0.02):
 
 @pytest.mark.parametrize("views,crop,seed", [(5, True, 0), (8, True, 2), (5, False, 3)])
 def test_fp32_end_to_end_matches_oracle(views, crop, seed):
-    m, ocfg, sd = build_pair(views, crop, "fp32", micro_batch=2, seed=seed)
-    x, bbox, intr = O.make_inputs(2, views, seed=100 + seed)
+    b = 4
+    m, ocfg, sd = build_pair(views, crop, "fp32", micro_batch=b, seed=seed)
+    x, bbox, intr = O.make_inputs(b, views, seed=100 + seed)
     ref, taps = O.forward(sd, ocfg, x, bbox if crop else None, intr if crop else None, return_taps=True)
     out = _forward(m, x, bbox, intr, crop)
     assert out["heatmap"].shape == ref["heatmap"].shape and out["joints_cam"].shape == ref["joints_cam"].shape
     assert rel_l2(out["heatmap"], ref["heatmap"]) < TOL["fp32"]
-    assert rel_l2(m.tensor_get("feat", 2), taps["backbone_out"]) < TOL["fp32"]
+    assert rel_l2(m.tensor_get("feat", b), taps["backbone_out"]) < TOL["fp32"]
     ok = _well_conditioned(ref["heatmap"])                       # [b, v, 21]
     assert ok.float().mean() > 0.8
     d2 = (out["joints_crop_img"] - ref["joints_crop_img"]).abs().amax(-1)
-    assert d2[ok].max() < 0.01                                   # crop-image pixels
-    tok = m.tensor_get("tokens", 2).cpu().reshape(2, views, 21, -1)
-    tref = taps["tokens_pe"].reshape(2, views, 21, -1)
+    assert d2[ok].max() < 0.05                                   # crop-image pixels
+    tok = m.tensor_get("tokens", b).cpu().reshape(b, views, 21, -1)
+    tref = taps["tokens_pe"].reshape(b, views, 21, -1)
     assert rel_l2(tok[ok], tref[ok]) < 5 * TOL["fp32"]
     sample_ok = ok.all(dim=(1, 2))
-    print(f"\n[fp32 e2e V={views}] well-conditioned joints {ok.float().mean():.3f}, samples fully conditioned {sample_ok.tolist()}")
-    for i in range(2):
+    errs_mm = (out["joints_cam"] - ref["joints_cam"]).abs().amax(dim=(1, 2)) * 1e3
+    print(f"\n[fp32 e2e V={views}] well-conditioned joints {ok.float().mean():.3f}, samples fully conditioned "
+          f"{sample_ok.tolist()}, max |joints_cam - oracle| per sample (mm) {[round(float(e), 5) for e in errs_mm]}")
+    fused = m.tensor_get("fused", b).cpu()
+    for i in range(b):
         if sample_ok[i]:
-            assert rel_l2(m.tensor_get("fused", 2)[i], taps["fused"][i]) < 5 * TOL["fp32"]
-            err_mm = (out["joints_cam"][i] - ref["joints_cam"][i]).abs().max().item() * 1e3
-            assert err_mm < 0.1, f"final keypoints differ by {err_mm} mm"
+            assert rel_l2(fused[i], taps["fused"][i]) < 5 * TOL["fp32"]
+            assert errs_mm[i] < 0.1, f"final keypoints differ by {errs_mm[i]} mm"
             assert rel_l2(out["joints_cam"][i], ref["joints_cam"][i]) < 1e-3
+    # even with near-tied joints (soft-argmax blends two pixels) the fp32 path stays well inside 0.1 mm here
+    assert errs_mm.max() < 0.1
 
 
 def test_fp32_matches_reference_golden_fixtures(golden_dir):

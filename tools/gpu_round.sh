@@ -1,18 +1,22 @@
 #!/bin/bash
-# tests + bench + ncu launch list on the GPU box
+# tests + bench + conv microbench (+ optional ncu) on the GPU box
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --no-header -rA -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" > gpurun_out/phases.txt
 tail -3 gpurun_out/pytest_gpu.log
-for mb in 16 32 64; do
-  timeout 600 python bench.py --steps 10 --warmup 3 --micro-batch $mb --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2>> gpurun_out/bench.err
+for mb in 32 64; do
+  timeout 600 python bench.py --steps 20 --warmup 5 --micro-batch $mb --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2>> gpurun_out/bench.err
   echo "bench mb$mb exit $?" >> gpurun_out/phases.txt
   cp gpurun_out/tc_launches.csv gpurun_out/tc_launches_mb$mb.csv 2>/dev/null
 done
+timeout 600 python tools/bench_conv.py 320 > gpurun_out/bench_conv.txt 2>&1
+cat gpurun_out/bench_conv.txt
 if [ "$1" == "ncu" ]; then
-timeout 600 python bench.py --steps 2 --warmup 3 --micro-batch 32 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 160 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --micro-batch 32 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-echo "ncu exit $?" >> gpurun_out/phases.txt
+for c in l3.conv3 l1.conv2 l1.down; do
+timeout 300 python tools/bench_conv.py 160 $c 1 > gpurun_out/plain_$c.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 1 -c 1 -o gpurun_out/prof_$c -f \
+    python tools/bench_conv.py 160 $c 1 > gpurun_out/ncu_$c.log 2>&1
+echo "ncu $c exit $?" >> gpurun_out/phases.txt
+done
 fi
-cat gpurun_out/phases.txt; cat gpurun_out/bench_mb32.json
+cat gpurun_out/phases.txt; cat gpurun_out/bench_mb64.json
