@@ -111,6 +111,7 @@ struct hmv_handle {
     bool bf16 = true;
     int V = 0, S = 0, d = 0, pitch = 576, feat = 512, hm = 32, img = 256;
     int mb = 0, mb_img = 0, num_sms = 148, esz = 2;
+    int fcap = 0;                                 // samples the fusion + graph-head stage handles per pass (>= mb)
     bool prepared = false;
     int64_t launches = 0;
     std::map<std::string, HostTensor> weights;
@@ -556,7 +557,7 @@ static int build_backbone(hmv_handle* h) {
 
 static int build_heads(hmv_handle* h) {
     const int hw = h->hm * h->hm;
-    const int rows_max = h->mb * h->S;
+    const int rows_max = h->fcap * h->S;
     const size_t e = h->esz;
     if (dev_alloc_t(h, &h->hm_int, static_cast<size_t>(h->mb_img) * kJoints * hw * 4)) return 1;
     if (dev_alloc_t(h, &h->xy, static_cast<size_t>(h->mb_img) * kJoints * 2 * 4)) return 1;
@@ -564,8 +565,8 @@ static int build_heads(hmv_handle* h) {
     if (dev_alloc_t(h, &h->wts, static_cast<size_t>(h->mb_img) * kJoints * 4 * 4)) return 1;
     if (dev_alloc_t(h, &h->bbox_int, static_cast<size_t>(h->mb_img) * 4 * 4)) return 1;
     if (dev_alloc_t(h, &h->intr_int, static_cast<size_t>(h->mb_img) * 4 * 4)) return 1;
-    if (dev_alloc_t(h, &h->joints_int, static_cast<size_t>(h->mb) * kJoints * 3 * 4)) return 1;
-    if (dev_alloc_t(h, &h->gcn_h1, static_cast<size_t>(h->mb) * kJoints * 256 * 4)) return 1;
+    if (dev_alloc_t(h, &h->joints_int, static_cast<size_t>(h->fcap) * kJoints * 3 * 4)) return 1;
+    if (dev_alloc_t(h, &h->gcn_h1, static_cast<size_t>(h->fcap) * kJoints * 256 * 4)) return 1;
     const size_t tokb = static_cast<size_t>(rows_max) * h->pitch;
     if (dev_alloc_t(h, &h->tok0_f32, tokb * 4) || dev_alloc_t(h, &h->tokA_f32, tokb * 4) || dev_alloc_t(h, &h->tokB_f32, tokb * 4) || dev_alloc_t(h, &h->ybuf, tokb * 4) ||
         dev_alloc_t(h, &h->hbuf, tokb * 4) || dev_alloc_t(h, &h->y2buf, tokb * 4))
@@ -673,7 +674,7 @@ static int build_heads(hmv_handle* h) {
         NEED(wo, p + ".to_out.weight"); NEED(bo, p + ".to_out.bias");
         NEED(w1, p + ".ff.net.1.weight"); NEED(b1, p + ".ff.net.1.bias");
         NEED(w2, p + ".ff.net.4.weight"); NEED(b2, p + ".ff.net.4.bias");
-        const int rows_in = h->mb * s_in, rows_q = h->mb * fp.nq;
+        const int rows_in = h->fcap * s_in, rows_q = h->fcap * fp.nq;
         if (add_linear(h, p + ".qkv", {wq, wk, wv}, nullptr, h->d, h->pitch, cur_l, rows_in,
                        make_ep(h->qkvbuf, 3072, lp_out, ACT_NONE), &fp.qkv)) return 1;
         Epilogue eo = make_ep(h->ybuf, h->pitch, OUT_F32_ROWMAJOR, ACT_NONE);
@@ -747,15 +748,17 @@ static int run_pose(hmv_handle* h, int n_img, float* heatmap_out, float* xy_scal
                              1000.f, static_cast<float>(h->img) / static_cast<float>(h->hm), s);
 }
 
+// tokens of this micro-batch are written at sample offset `off` of the (fusion-pass wide) token stream
 template <typename T>
-static int run_sample_t(hmv_handle* h, int n_img, const float* bbox, const float* intr, cudaStream_t s) {
+static int run_sample_t(hmv_handle* h, int n_img, const float* bbox, const float* intr, cudaStream_t s, int off = 0) {
     h->launches += 2;
     if (sample_gather_launch<T>(static_cast<const T*>(h->featbuf), h->xy, static_cast<T*>(h->bufT2), h->wts, n_img, h->hm, h->hm, 1024, s)) return 1;
     if (run_layer(h, h->layers[h->samp], n_img * kJoints * 4, s)) return 1;
     TokenParams tp{};
     tp.g = static_cast<const float*>(h->bufDS); tp.ldg = 512; tp.wts = h->wts; tp.xy = h->xy;
     tp.bbox = bbox; tp.intr = intr; tp.pe = h->cfg.use_sin ? h->pe : nullptr;
-    tp.tok_f32 = h->tok0_f32; tp.tok_lp = h->tok0_lp;
+    const size_t tok_off = static_cast<size_t>(off) * h->S * h->pitch;
+    tp.tok_f32 = h->tok0_f32 + tok_off; tp.tok_lp = static_cast<T*>(h->tok0_lp) + tok_off;
     tp.n_img = n_img; tp.feat = h->feat; tp.d = h->d; tp.pitch = h->pitch; tp.tokens_per_sample = h->S;
     tp.use_pos2d = h->cfg.use_pos2d; tp.use_crop = h->cfg.use_crop;
     return tokens_launch<T>(tp, s);
@@ -789,13 +792,17 @@ static int run_gcn(hmv_handle* h, int n, float* out, cudaStream_t s) {
     return gcn_launch(g, h->gcn_h1, s);
 }
 
-// one micro-batch of n <= mb samples, all pointers already offset
-static int run_chunk(hmv_handle* h, const float* x, const float* bbox, const float* intr, int n, float* heatmap,
-                     float* xy_scaled, float* joints, cudaStream_t s) {
+// front half for one micro-batch of n <= mb samples (pointers already offset): backbone, pose_net, soft-argmax,
+// sampling and token assembly; its tokens land at sample offset `off` of the current fusion pass
+static int run_front(hmv_handle* h, const float* x, const float* bbox, const float* intr, int n, int off, float* heatmap,
+                     float* xy_scaled, cudaStream_t s) {
     const int n_img = n * h->V;
     if (run_backbone(h, x, n_img, -1, s)) return 1;
     if (run_pose(h, n_img, heatmap, xy_scaled, s)) return 1;
-    if (h->bf16 ? run_sample_t<bf16>(h, n_img, bbox, intr, s) : run_sample_t<float>(h, n_img, bbox, intr, s)) return 1;
+    return h->bf16 ? run_sample_t<bf16>(h, n_img, bbox, intr, s, off) : run_sample_t<float>(h, n_img, bbox, intr, s, off);
+}
+// back half for n <= fcap samples: fusion transformer + graph head (small, latency-bound kernels: run once per pass)
+static int run_back(hmv_handle* h, int n, float* joints, cudaStream_t s) {
     if (h->bf16 ? run_fusion_t<bf16>(h, n, s) : run_fusion_t<float>(h, n, s)) return 1;
     return run_gcn(h, n, joints, s);
 }
@@ -844,6 +851,7 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     h->d = h->feat + (cfg->use_pos2d ? 2 : 0) + (cfg->use_crop ? 10 : 0);
     h->pitch = (h->d + 63) / 64 * 64;
     h->mb = cfg->micro_batch; h->mb_img = h->mb * h->V;
+    h->fcap = h->mb >= 256 ? h->mb : (256 / h->mb) * h->mb;          // a multiple of the micro-batch
     h->num_sms = prop.multiProcessorCount;
     if (cudaHostAlloc(reinterpret_cast<void**>(&h->err_flag_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_flag_dev), h->err_flag_host, 0) != cudaSuccess) {
@@ -913,14 +921,17 @@ int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* i
     if (hmv::check_flag(h)) return 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t per_sample_x = static_cast<size_t>(h->V) * 3 * h->img * h->img;
-    for (int s0 = 0; s0 < batch; s0 += h->mb) {
-        const int n = batch - s0 < h->mb ? batch - s0 : h->mb;
-        if (hmv::run_chunk(h, x + s0 * per_sample_x, bbox ? bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
-                           intr ? intr + static_cast<size_t>(s0) * h->V * 4 : nullptr, n,
-                           heatmap ? heatmap + static_cast<size_t>(s0) * h->V * 21 * h->hm * h->hm : nullptr,
-                           joints_crop_img ? joints_crop_img + static_cast<size_t>(s0) * h->V * 21 * 2 : nullptr,
-                           joints_cam ? joints_cam + static_cast<size_t>(s0) * 21 * 3 : nullptr, s))
-            return 1;
+    for (int p0 = 0; p0 < batch; p0 += h->fcap) {                     // fusion passes
+        const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
+        for (int s0 = p0; s0 < p0 + np; s0 += h->mb) {                // backbone micro-batches
+            const int n = p0 + np - s0 < h->mb ? p0 + np - s0 : h->mb;
+            if (hmv::run_front(h, x + s0 * per_sample_x, bbox ? bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
+                               intr ? intr + static_cast<size_t>(s0) * h->V * 4 : nullptr, n, s0 - p0,
+                               heatmap ? heatmap + static_cast<size_t>(s0) * h->V * 21 * h->hm * h->hm : nullptr,
+                               joints_crop_img ? joints_crop_img + static_cast<size_t>(s0) * h->V * 21 * 2 : nullptr, s))
+                return 1;
+        }
+        if (hmv::run_back(h, np, joints_cam ? joints_cam + static_cast<size_t>(p0) * 21 * 3 : nullptr, s)) return 1;
     }
     return 0;
 }
@@ -974,19 +985,23 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
         HMV_CUDA(cudaMemcpyAsync(h->d_intr, intr, nimg * 4 * sizeof(float), cudaMemcpyHostToDevice, ks));
     }
     int chunk = 0;
-    for (int s0 = 0; s0 < batch; s0 += h->mb, ++chunk) {
-        const int n = batch - s0 < h->mb ? batch - s0 : h->mb;
-        const int b = chunk & 1;
-        if (chunk >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
-        HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x + s0 * per_sample_x, per_sample_x * n * sizeof(float), cudaMemcpyHostToDevice, cs));
-        HMV_CUDA(cudaEventRecord(h->ev_copied[b], cs));
-        HMV_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[b], 0));
-        if (hmv::run_chunk(h, h->xstage[b], h->cfg.use_crop ? h->d_bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
-                           h->cfg.use_crop ? h->d_intr + static_cast<size_t>(s0) * h->V * 4 : nullptr, n,
-                           h->d_hm + static_cast<size_t>(s0) * h->V * 21 * h->hm * h->hm,
-                           h->d_xy + static_cast<size_t>(s0) * h->V * 21 * 2, h->d_j + static_cast<size_t>(s0) * 21 * 3, ks))
-            return 1;
-        HMV_CUDA(cudaEventRecord(h->ev_consumed[b], ks));
+    for (int p0 = 0; p0 < batch; p0 += h->fcap) {
+        const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
+        for (int s0 = p0; s0 < p0 + np; s0 += h->mb, ++chunk) {
+            const int n = p0 + np - s0 < h->mb ? p0 + np - s0 : h->mb;
+            const int b = chunk & 1;
+            if (chunk >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
+            HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x + s0 * per_sample_x, per_sample_x * n * sizeof(float), cudaMemcpyHostToDevice, cs));
+            HMV_CUDA(cudaEventRecord(h->ev_copied[b], cs));
+            HMV_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[b], 0));
+            if (hmv::run_front(h, h->xstage[b], h->cfg.use_crop ? h->d_bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
+                               h->cfg.use_crop ? h->d_intr + static_cast<size_t>(s0) * h->V * 4 : nullptr, n, s0 - p0,
+                               h->d_hm + static_cast<size_t>(s0) * h->V * 21 * h->hm * h->hm,
+                               h->d_xy + static_cast<size_t>(s0) * h->V * 21 * 2, ks))
+                return 1;
+            HMV_CUDA(cudaEventRecord(h->ev_consumed[b], ks));
+        }
+        if (hmv::run_back(h, np, h->d_j + static_cast<size_t>(p0) * 21 * 3, ks)) return 1;
     }
     if (heatmap) HMV_CUDA(cudaMemcpyAsync(heatmap, h->d_hm, nimg * 21 * h->hm * h->hm * sizeof(float), cudaMemcpyDeviceToHost, ks));
     if (joints_crop_img) HMV_CUDA(cudaMemcpyAsync(joints_crop_img, h->d_xy, nimg * 21 * 2 * sizeof(float), cudaMemcpyDeviceToHost, ks));

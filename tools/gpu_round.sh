@@ -8,6 +8,7 @@ for mb in 32 64; do
   timeout 600 python bench.py --steps 20 --warmup 5 --micro-batch $mb --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2>> gpurun_out/bench.err
   echo "bench mb$mb exit $?" >> gpurun_out/phases.txt
   cp gpurun_out/tc_launches.csv gpurun_out/tc_launches_mb$mb.csv 2>/dev/null
+  timeout 600 python bench.py --steps 20 --warmup 5 --micro-batch $mb --no-cpu-baseline --no-clocks > gpurun_out/bench_mb${mb}_noclk.json 2>> gpurun_out/bench.err
 done
 timeout 600 python tools/bench_conv.py 320 > gpurun_out/bench_conv.txt 2>&1
 cat gpurun_out/bench_conv.txt
@@ -19,4 +20,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
 echo "ncu $c exit $?" >> gpurun_out/phases.txt
 done
 fi
-cat gpurun_out/phases.txt; cat gpurun_out/bench_mb64.json
+cat gpurun_out/phases.txt; for f in gpurun_out/bench_mb*.json; do echo $f; python -c "
+import json,sys
+d=json.load(open('$f'))
+print('value %.0f e2e %.0f ms %.2f tc_frac %.3f share %.2f tc_ms %.2f'%(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_share_of_step'], d['roofline']['kernel_ms_per_step']), d['clocks'])
+"; done
