@@ -175,6 +175,12 @@ def run_own(args):
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.no_clocks:
         sampler.start()
+    # clock ramp: a GPU coming out of idle needs ~1 s of load before it holds its boost clocks; this pre-warm is
+    # not counted as one of the W warm-up steps
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < args.ramp_seconds:
+        step()
+        torch.cuda.synchronize(dev)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -263,6 +269,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi clock sampler")
+    ap.add_argument("--ramp-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

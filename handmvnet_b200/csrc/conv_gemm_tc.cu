@@ -133,6 +133,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// two fp32 -> packed bf16x2 (lo in the low half), optionally clamped at zero in the same instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, bool relu) {
+    uint32_t d;
+    if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -261,11 +274,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4);
+            mbar_init(tempty0 + 8 * i, MODE == TC_DIRECT ? 4 : 8);     // one arrival per epilogue warp
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(cfull0 + 8 * i, 1);
-            mbar_init(cempty0 + 8 * i, 4);
+            mbar_init(cempty0 + 8 * i, 8);
         }
         fence_barrier_init();
     }
@@ -345,7 +358,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp == 6) {
+    } else if (warp == 2) {
         // ===================== residual producer (TC_STORE_RES with a bf16 residual) =====================
         if (MODE == TC_STORE_RES && has_res && lane == 0) {
             uint32_t g = 0;
@@ -364,112 +377,125 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
-    } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    } else if (MODE == TC_DIRECT && warp >= 4 && warp < 8) {
+        // ===================== direct epilogue (4 warps, one TMEM lane quarter each) =====================
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.num_n_tiles;
+            const int m_tile = tile / p.num_n_tiles;
+            if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) break;
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            const int row = m_tile * kTcBlockM + quarter * 32 + lane;
+            const bool row_ok = row < p.ep.M;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(t0 + c, r0);
+                if (c + 16 < BN) tmem_ld16(t0 + c + 16, r1);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
+                if (c + 16 < BN) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (MODE != TC_DIRECT && warp >= 4) {
+        // ===================== TMA-store epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+        // Each 64-column chunk of the tile is staged as [128 rows][128 B] (128B swizzle); a quarter's 32-row slab is
+        // written by its two warps (32 columns each) and stored by lane 0 of the first one.
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const bool issuer = half == 0 && lane == 0;
+        const bool relu = p.ep.act == ACT_RELU;
+        const bool gelu = p.ep.act == ACT_GELU;
+        int acc = 0;
+        uint32_t acc_phase = 0;
         bool alive = true;
-        uint32_t g = 0;                                    // running chunk counter (TMA-store modes)
+        uint32_t g = 0;                                    // running chunk counter
         for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = tile / p.num_n_tiles;
             if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) { alive = false; break; }
             tc_fence_after();
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            if constexpr (MODE == TC_DIRECT) {
-                const int row = m_tile * kTcBlockM + quarter * 32 + lane;
-                const bool row_ok = row < p.ep.M;
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 32;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(t0 + c, r0);
-                    if (c + 16 < BN) tmem_ld16(t0 + c + 16, r1);
-                    tmem_ld_wait();
-                    float v[16];
+            for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
+                constexpr uint32_t S = Cfg::kNumS > 0 ? Cfg::kNumS : 1, R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
+                const uint32_t sslot = g % S, rslot = g % R;
+                if (issuer) bulk_wait_read<(Cfg::kNumS > 0 ? Cfg::kNumS - 1 : 0)>();   // the slab's previous store left smem
+                named_bar_sync(1 + quarter, 64);
+                uint32_t r[32];
+                tmem_ld32(t0 + c * kChunkCols, r);
+                const int col0 = n_tile * BN + c * kChunkCols + half * 32;
+                float4 bq[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
-                    if (c + 16 < BN) {
+                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + j);
+                const uint32_t slab_off = Cfg::kStages * Cfg::kStageBytes + quarter * (32 * 128) + lane * 128;
+                uint4 rq[4];
+                if (has_res) {
+                    if (!mbar_wait(cfull0 + 8 * rslot, (g / R) & 1, p.err_flag, 6)) { alive = false; }
+                    const uint8_t* rrow = smem + slab_off + (Cfg::kNumS + rslot) * kChunkBytes;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
-                        if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        rq[j] = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            } else {
-                const int act = p.ep.act;
-#pragma unroll 1
-                for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
-                    constexpr uint32_t S = Cfg::kNumS > 0 ? Cfg::kNumS : 1, R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
-                    const uint32_t sslot = g % S, rslot = g % R;
-                    if (lane == 0) bulk_wait_read<(Cfg::kNumS > 0 ? Cfg::kNumS - 1 : 0)>();   // my slab's previous store left smem
+                tmem_ld_wait();
+                if (c == BN / kChunkCols - 1) {                // accumulator drained: hand TMEM back early
+                    tc_fence_before();
                     __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                }
+                uint8_t* srow = smem + slab_off + sslot * kChunkBytes;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                  // 4 x (8 columns = 16 bytes)
+                    float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
+                    float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
+                    float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
+                    float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
                     if (has_res) {
-                        if (!mbar_wait(cfull0 + 8 * rslot, (g / R) & 1, p.err_flag, 6)) { alive = false; break; }
+                        v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
+                        v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
                     }
-                    const uint32_t slab = sbuf0 + sslot * kChunkBytes + quarter * (32 * 128);
-                    const uint32_t rowaddr = slab + lane * 128;
-                    const uint32_t resaddr = rbuf0 + rslot * kChunkBytes + quarter * (32 * 128) + lane * 128;
-                    const int col0 = n_tile * BN + c * kChunkCols;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t r[32];
-                        tmem_ld32(t0 + c * kChunkCols + hf * 32, r);
-                        tmem_ld_wait();
-                        if (c == BN / kChunkCols - 1 && hf == 1) {           // accumulator drained: hand TMEM back early
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {                        // 4 x (8 columns = 16 bytes)
-                            float v[8];
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + hf * 32 + j * 8));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + hf * 32 + j * 8 + 4));
-                            v[0] = __uint_as_float(r[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[j * 8 + 1]) + b0.y;
-                            v[2] = __uint_as_float(r[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[j * 8 + 3]) + b0.w;
-                            v[4] = __uint_as_float(r[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[j * 8 + 5]) + b1.y;
-                            v[6] = __uint_as_float(r[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[j * 8 + 7]) + b1.w;
-                            const uint32_t sw = (static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4;              // 128B swizzle
-                            const uint32_t a = rowaddr + sw;
-                            if (has_res) {
-                                const uint4 q = lds128(resaddr + sw);
-                                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-                                v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
-                                v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
-                            }
-                            if (act == ACT_RELU) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-                            } else if (act == ACT_GELU) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                            sts128(a, o);
-                        }
+                    if (gelu) {
+                        v0.x = gelu_erf(v0.x); v0.y = gelu_erf(v0.y); v1.x = gelu_erf(v1.x); v1.y = gelu_erf(v1.y);
+                        v2.x = gelu_erf(v2.x); v2.y = gelu_erf(v2.y); v3.x = gelu_erf(v3.x); v3.y = gelu_erf(v3.y);
                     }
-                    fence_async_smem();                    // generic-proxy smem writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (has_res) mbar_arrive(cempty0 + 8 * rslot);        // residual slot consumed by this warp
-                        tma_store_2d(&tmC, slab, col0, m_tile * kTcBlockM + quarter * 32);
-                        bulk_commit();
-                    }
+                    uint4 o;
+                    o.x = cvt_bf16x2(v0.x, v0.y, relu); o.y = cvt_bf16x2(v1.x, v1.y, relu);
+                    o.z = cvt_bf16x2(v2.x, v2.y, relu); o.w = cvt_bf16x2(v3.x, v3.y, relu);
+                    *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4)) = o;   // 128B swizzle
                 }
+                fence_async_smem();                        // generic-proxy smem writes -> visible to the TMA engine
+                if (has_res) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(cempty0 + 8 * rslot);          // residual slot consumed by this warp
+                }
+                named_bar_sync(1 + quarter, 64);           // both column halves of the slab are written
+                if (issuer) {
+                    tma_store_2d(&tmC, sbuf0 + sslot * kChunkBytes + quarter * (32 * 128), n_tile * BN + c * kChunkCols,
+                                 m_tile * kTcBlockM + quarter * 32);
+                    bulk_commit();
+                }
+                if (!alive) break;
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if constexpr (MODE != TC_DIRECT) {
-            if (lane == 0) bulk_wait_read<0>();             // staged data must stay valid until every store has read it
-            __syncwarp();
-        }
+        if (issuer) bulk_wait_read<0>();                   // staged data must stay valid until every store has read it
+        __syncwarp();
     }
 
     tc_fence_before();

@@ -24,7 +24,7 @@ namespace hmv {
 constexpr int kTcBlockM = 128;
 constexpr int kTcBlockK = 64;          // bf16 elements -> 128 B = one swizzle-128B row
 constexpr int kTcUmmaK = 16;
-constexpr int kTcThreads = 224;        // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue, warp6 residual TMA
+constexpr int kTcThreads = 384;        // warp0 TMA, warp1 MMA + TMEM alloc, warp2 residual TMA, warps 4-11 epilogue
 constexpr int kTcMaxTaps = 9;
 
 struct TcTap { int c_off, dw, a, dh; };

@@ -375,6 +375,170 @@ template int attention_launch<bf16>(const bf16*, int, bf16*, int, int, int, int,
 template int attention_launch<float>(const float*, int, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
+// bf16 attention core on the tensor cores (mma.sync m16n8k16, fp32 accumulate), flash-style:
+// one CTA = 64 queries of one (sample, head); K/V stream through shared memory in blocks of 64 keys with an
+// online softmax, so any key count (21 .. 336 for 1 .. 16 views) runs with bounded registers.
+// (reference layers.py:217-223; the fp32 check mode keeps the scalar kernel above.)
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kAttQ = 64, kAttK = 64, kAttD = 128, kAttPitch = kAttD + 8;     // +8 bf16: conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 64 rows x 128 bf16 from global (row pitch ld) into padded smem; rows >= valid are zero filled
+__device__ __forceinline__ void att_load_tile(bf16* dst, const bf16* src, int ld, int valid) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 128) {
+        const int r = i >> 4, c = (i & 15) * 8;
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * kAttPitch + c));
+        if (r < valid) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + static_cast<size_t>(r) * ld + c) : "memory");
+        } else {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0u) : "memory");
+        }
+    }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out, int ld_out, int tokens_per_sample,
+                     int q_row0, int nq, int kv_row0, int nk, int heads, float scale_log2e) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    bf16* qs = reinterpret_cast<bf16*>(att_smem);
+    bf16* ks = qs + kAttQ * kAttPitch;
+    bf16* vs = ks + kAttK * kAttPitch;
+    const int b = blockIdx.x, h = blockIdx.y, q0 = blockIdx.z * kAttQ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int inner = heads * kAttD;
+    const bf16* qbase = qkv + (static_cast<size_t>(b) * tokens_per_sample + q_row0 + q0) * ld + h * kAttD;
+    const bf16* kbase = qkv + (static_cast<size_t>(b) * tokens_per_sample + kv_row0) * ld + inner + h * kAttD;
+    const bf16* vbase = kbase + inner;
+
+    att_load_tile(qs, qbase, ld, nq - q0 < kAttQ ? nq - q0 : kAttQ);
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // rows g and g+8 of this warp's 16-row slab
+
+    const uint32_t qs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(qs));
+    const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(ks));
+    const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(vs));
+    // ldmatrix lane addressing: A (Q): lanes 0-15 rows 0-15 @k, lanes 16-31 rows 0-15 @k+8
+    const uint32_t a_off = ((warp * 16 + (lane & 15)) * kAttPitch + (lane >> 4) * 8) * 2;
+    // B (K): matrices (keys j..j+7 @k), (j..j+7 @k+8), (j+8..15 @k), (j+8..15 @k+8)
+    const uint32_t bk_off = (((lane & 7) + (lane >> 4) * 8) * kAttPitch + ((lane >> 3) & 1) * 8) * 2;
+    // B (V, transposed): matrices (keys j..j+7 @d), (j+8..15 @d), (j..j+7 @d+8), (j+8..15 @d+8)
+    const uint32_t bv_off = (((lane & 7) + ((lane >> 3) & 1) * 8) * kAttPitch + (lane >> 4) * 8) * 2;
+
+    for (int j0 = 0; j0 < nk; j0 += kAttK) {
+        __syncthreads();                                           // previous block fully consumed
+        const int kvalid = nk - j0 < kAttK ? nk - j0 : kAttK;
+        att_load_tile(ks, kbase + static_cast<size_t>(j0) * ld, ld, kvalid);
+        att_load_tile(vs, vbase + static_cast<size_t>(j0) * ld, ld, kvalid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- S = Q K^T for this warp's 16 queries x 64 keys ----
+        float sc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < kAttD / 16; ++kk) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(qs_addr + a_off + kk * 32, a0, a1, a2, a3);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {                       // pairs of 8-key tiles
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(ks_addr + bk_off + np * 16 * kAttPitch * 2 + kk * 32, b0, b1, b2, b3);
+                mma_bf16(sc[2 * np], a0, a1, a2, a3, b0, b1);
+                mma_bf16(sc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+        // ---- online softmax (rows g, g+8; key columns nt*8 + 2t, +1) ----
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * t;
+            if (c >= kvalid) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+            if (c + 1 >= kvalid) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+            bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+            bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+        const float al0 = exp2f((m0 - mn0) * scale_log2e), al1 = exp2f((m1 - mn1) * scale_log2e);
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t pa[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = exp2f((sc[nt][0] - mn0) * scale_log2e), p1 = exp2f((sc[nt][1] - mn0) * scale_log2e);
+            const float p2 = exp2f((sc[nt][2] - mn1) * scale_log2e), p3 = exp2f((sc[nt][3] - mn1) * scale_log2e);
+            rs0 += p0 + p1; rs1 += p2 + p3;
+            pa[nt][0] = pack_bf16x2(p0, p1);
+            pa[nt][1] = pack_bf16x2(p2, p3);
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+        // ---- O += P V ----
+#pragma unroll
+        for (int kk = 0; kk < kAttK / 16; ++kk) {
+            const uint32_t a0 = pa[2 * kk][0], a1 = pa[2 * kk][1], a2 = pa[2 * kk + 1][0], a3 = pa[2 * kk + 1][1];
+#pragma unroll
+            for (int dp = 0; dp < 8; ++dp) {                       // pairs of 8-wide d tiles
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_trans(vs_addr + bv_off + kk * 16 * kAttPitch * 2 + dp * 32, b0, b1, b2, b3);
+                mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
+                mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int dt = 0; dt < 16; ++dt) {
+        const int d = dt * 8 + 2 * t;
+        if (r0 < nq)
+            *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + r0) * ld_out + h * kAttD + d) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (r1 < nq)
+            *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * nq + r1) * ld_out + h * kAttD + d) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+}
+
+int attention_mma_launch(const bf16* qkv, int ld, bf16* out, int ld_out, int batch, int tokens_per_sample, int q_row0,
+                         int nq, int kv_row0, int nk, int heads, int dim_head, float scale, cudaStream_t s) {
+    if (batch == 0) return 0;
+    HMV_CHECK(dim_head == kAttD, "attention: dim_head must be 128");
+    HMV_CHECK(nk > 0 && nq > 0 && ld % 8 == 0 && ld_out % 2 == 0, "attention: bad shape");
+    const int smem = (kAttQ + 2 * kAttK) * kAttPitch * 2;
+    static bool configured = false;
+    if (!configured) {
+        HMV_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    attention_mma_kernel<<<dim3(batch, heads, (nq + kAttQ - 1) / kAttQ), 128, smem, s>>>(
+        qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq, kv_row0, nk, heads, scale * 1.4426950408889634f);
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm (optionally two chained LayerNorms): one warp per row, values kept in registers
 // ------------------------------------------------------------------------------------------------
 template <typename T>

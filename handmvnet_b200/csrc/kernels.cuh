@@ -55,6 +55,10 @@ template <typename T>
 int attention_launch(const T* qkv, int ld, T* out, int ld_out, int batch, int tokens_per_sample, int q_row0, int nq,
                      int kv_row0, int nk, int heads, int dim_head, float scale, cudaStream_t s);
 
+// bf16 tensor-core (mma.sync) flash-style variant used on the bf16 path
+int attention_mma_launch(const bf16* qkv, int ld, bf16* out, int ld_out, int batch, int tokens_per_sample, int q_row0,
+                         int nq, int kv_row0, int nk, int heads, int dim_head, float scale, cudaStream_t s);
+
 // h = LN(in; g1,b1) -> out_f32 ; out_lp = g2 ? LN(h; g2,b2) : h   (reference layers.py:228,165,233)
 template <typename T>
 int layernorm_launch(const float* in, int ld_in, const float* g1, const float* b1, float* out_f32, int ld_out,

@@ -770,8 +770,13 @@ static int run_fusion_t(hmv_handle* h, int n, cudaStream_t s) {
         const int rows_in = n * fp.s_in, rows_q = n * fp.nq;
         if (run_layer(h, h->layers[fp.qkv], rows_in, s)) return 1;
         h->launches += 3;
-        if (attention_launch<T>(static_cast<const T*>(h->qkvbuf), 3072, static_cast<T*>(h->attbuf), 1024, n, fp.s_in, 0, fp.nq,
-                                fp.kv_row0, fp.nk, 8, 128, 0.08838834764831845f /* 128^-0.5 */, s)) return 1;
+        if constexpr (sizeof(T) == 2) {
+            if (attention_mma_launch(static_cast<const bf16*>(h->qkvbuf), 3072, static_cast<bf16*>(h->attbuf), 1024, n, fp.s_in, 0,
+                                     fp.nq, fp.kv_row0, fp.nk, 8, 128, 0.08838834764831845f /* 128^-0.5 */, s)) return 1;
+        } else {
+            if (attention_launch<T>(static_cast<const T*>(h->qkvbuf), 3072, static_cast<T*>(h->attbuf), 1024, n, fp.s_in, 0, fp.nq,
+                                    fp.kv_row0, fp.nk, 8, 128, 0.08838834764831845f /* 128^-0.5 */, s)) return 1;
+        }
         if (run_layer(h, h->layers[fp.outp], rows_q, s)) return 1;
         if (layernorm_launch<T>(h->ybuf, h->pitch, fp.g1, fp.b1, h->hbuf, h->pitch, fp.gff, fp.bff, static_cast<T*>(h->hnbuf),
                                 h->pitch, rows_q, h->d, 1e-5f, s)) return 1;
