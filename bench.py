@@ -187,12 +187,18 @@ def run_own(args):
     launches0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    t_enq = time.perf_counter()
+    for i in range(args.steps):
         out = step()
+        marks[i + 1].record()
+    enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / args.steps
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    step_ms = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = model.launch_count() - launches0
     assert torch.isfinite(out["joints_cam"]).all()
 
@@ -216,6 +222,7 @@ def run_own(args):
         model(x, bbox, cam)
     csv = os.path.join(ROOT, "gpurun_out", "tc_launches.csv") if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     tc_ms, tc_flops, tc_n = model.profile_read(csv)
+    phases = {k: v / args.steps for k, v in model.profile_phases().items()}
     model.profile(False)
     clocks = sampler.stop() if rank == 0 else None      # samples cover warm-up, timed, e2e and profiling passes
 
@@ -229,7 +236,9 @@ def run_own(args):
         achieved = tc_flops / (tc_ms * 1e-3) * 1e-12 if tc_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps,
+            "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"HO3D_HandMvNet release config, synthetic 5-view B={B} per GPU, bf16, random-init weights",
                        "views": views, "image": 256, "batch_per_gpu": B, "micro_batch": args.micro_batch,
@@ -247,7 +256,8 @@ def run_own(args):
                          "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps,
                          "kernel_share_of_step": (tc_ms / args.steps) / (dev_ms / args.steps),
                          "timing": "second pass over the same steps with CUDA events around every launch",
-                         "end_to_end_model_tflops": FLOP_PER_SAMPLE_V5 * value / world * 1e-12},
+                         "end_to_end_model_tflops": FLOP_PER_SAMPLE_V5 * value / world * 1e-12,
+                         "phase_ms_per_step": phases},
         }
         if world == 1 and not args.no_cpu_baseline:
             ps, ms, cores = cpu_oracle_throughput(1, 12, 3)

@@ -12,7 +12,7 @@ TENSOR = {"feat": 0, "heatmap": 1, "xy": 2, "tokens": 3, "fused": 4, "joints": 5
 # every symbol include/handmvnet_b200.h declares
 EXPORTS = ["hmv_create", "hmv_destroy", "hmv_set_weight", "hmv_prepare", "hmv_forward", "hmv_forward_host",
            "hmv_synchronize", "hmv_stage_run", "hmv_tensor_get", "hmv_tensor_set", "hmv_debug_backbone",
-           "hmv_debug_num_steps", "hmv_debug_step_name", "hmv_conv_bn_act", "hmv_profile_enable", "hmv_profile_read",
+           "hmv_debug_num_steps", "hmv_debug_step_name", "hmv_conv_bn_act", "hmv_profile_enable", "hmv_profile_read", "hmv_profile_phases",
            "hmv_launch_count", "hmv_num_sms",
            "hmv_last_error", "hmv_version"]
 
@@ -56,6 +56,7 @@ def load():
     lib.hmv_profile_enable.argtypes = [vp, i32]
     lib.hmv_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(i64), ctypes.c_char_p]
+    lib.hmv_profile_phases.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.hmv_launch_count.argtypes = [vp]
     lib.hmv_launch_count.restype = i64
     lib.hmv_num_sms.argtypes = [vp]

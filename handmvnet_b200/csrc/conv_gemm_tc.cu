@@ -292,6 +292,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();                        // everything above overlapped the previous kernel; its results are visible from here
+    pdl_launch_dependents();
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = p.num_taps * p.cblks;
@@ -595,8 +597,8 @@ template <int BN, int MODE>
 static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    conv_gemm_tc_kernel<BN, MODE><<<grid, kTcThreads, TcCfg<BN, MODE>::kSmemBytes, stream>>>(l.tmA, l.tmB, l.tmC, l.tmR, l.p);
-    HMV_CUDA(cudaGetLastError());
+    HMV_CUDA(launch_kernel(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(kTcThreads), TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB,
+                           l.tmC, l.tmR, l.p));
     return 0;
 }
 

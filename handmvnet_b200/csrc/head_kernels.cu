@@ -12,6 +12,7 @@ namespace hmv {
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int H, int W, int Hp, int Wp,
                                   int pad, size_t total) {
+    pdl_wait();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int wp = static_cast<int>(idx % Wp);
@@ -39,7 +40,7 @@ template <typename T>
 int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, int Wp, int pad, cudaStream_t s) {
     const size_t total = static_cast<size_t>(n_img) * Hp * Wp;
     if (total == 0) return 0;
-    pack_input_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, out, H, W, Hp, Wp, pad, total);
+    HMV_CUDA(launch_kernel(pack_input_kernel<T>, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, x, out, H, W, Hp, Wp, pad, total));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -52,6 +53,7 @@ template int pack_input_launch<float>(const float*, float*, int, int, int, int, 
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, int Win, int Hout, int Wout,
                                int C, size_t total) {
+    pdl_wait();
     constexpr int VEC = 16 / sizeof(T);
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -103,7 +105,7 @@ int maxpool_launch(const T* in, T* out, int n_img, int Hin, int Win, int C, cuda
     const int Hout = (Hin + 2 - 3) / 2 + 1, Wout = (Win + 2 - 3) / 2 + 1;
     const size_t total = static_cast<size_t>(n_img) * Hout * Wout * (C / VEC);
     if (total == 0) return 0;
-    maxpool_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, Hin, Win, Hout, Wout, C, total);
+    HMV_CUDA(launch_kernel(maxpool_kernel<T>, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, in, out, Hin, Win, Hout, Wout, C, total));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -115,6 +117,7 @@ template int maxpool_launch<float>(const float*, float*, int, int, int, int, cud
 // ------------------------------------------------------------------------------------------------
 __global__ void softargmax_kernel(const float* __restrict__ hm, float* __restrict__ xy, float* __restrict__ xy_scaled,
                                   int n_maps, int H, int W, float temperature, float scale) {
+    pdl_wait();
     const int map = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (map >= n_maps) return;
@@ -152,7 +155,7 @@ int softargmax_launch(const float* hm, float* xy, float* xy_scaled, int n_maps, 
                       float scale, cudaStream_t s) {
     if (n_maps == 0) return 0;
     HMV_CHECK((H * W) % 4 == 0, "softargmax: H*W must be a multiple of 4");
-    softargmax_kernel<<<(n_maps + 7) / 8, 256, 0, s>>>(hm, xy, xy_scaled, n_maps, H, W, temperature, scale);
+    HMV_CUDA(launch_kernel(softargmax_kernel, dim3((n_maps + 7) / 8), dim3(256), 0, s, hm, xy, xy_scaled, n_maps, H, W, temperature, scale));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -163,6 +166,7 @@ int softargmax_launch(const float* hm, float* xy, float* xy_scaled, int n_maps, 
 template <typename T>
 __global__ void sample_gather_kernel(const T* __restrict__ feat, const float* __restrict__ xy, T* __restrict__ rows,
                                      float* __restrict__ wts, int H, int W, int C) {
+    pdl_wait();
     const int nj = blockIdx.x;                 // n * 21 + j
     const int n = nj / kJoints;
     const float x = xy[2 * nj], y = xy[2 * nj + 1];
@@ -194,7 +198,7 @@ int sample_gather_launch(const T* feat, const float* xy, T* rows, float* wts, in
                          cudaStream_t s) {
     if (n_img == 0) return 0;
     HMV_CHECK((C * sizeof(T)) % 16 == 0, "sample_gather: row must be a multiple of 16 bytes");
-    sample_gather_kernel<T><<<n_img * kJoints, 128, 0, s>>>(feat, xy, rows, wts, H, W, C);
+    HMV_CUDA(launch_kernel(sample_gather_kernel<T>, dim3(n_img * kJoints), dim3(128), 0, s, feat, xy, rows, wts, H, W, C));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -207,6 +211,7 @@ template int sample_gather_launch<float>(const float*, const float*, float*, flo
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void tokens_kernel(const TokenParams p) {
+    pdl_wait();
     const int row = blockIdx.x;                // n * 21 + j
     const int n = row / kJoints;
     const int pos = row % p.tokens_per_sample; // token index inside the sample (view-major)
@@ -249,7 +254,7 @@ template <typename T>
 int tokens_launch(const TokenParams& p, cudaStream_t s) {
     if (p.n_img == 0) return 0;
     HMV_CHECK(!p.use_crop || (p.bbox && p.intr), "tokens: 'crop' positional encoding needs bbox and intrinsics");
-    tokens_kernel<T><<<p.n_img * kJoints, 128, 0, s>>>(p);
+    HMV_CUDA(launch_kernel(tokens_kernel<T>, dim3(p.n_img * kJoints), dim3(128), 0, s, p));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -263,6 +268,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attention_kernel(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out, int tokens_per_sample,
                  int q_row0, int nq, int kv_row0, int nk, int heads, float scale) {
+    pdl_wait();
     constexpr int DH = 128;
     constexpr int PK = DH + (sizeof(T) == 2 ? 2 : 1);      // padded K pitch: conflict-free lane-per-key reads
     constexpr int MAXJ = 11;                               // keys per lane: nk <= 352
@@ -366,8 +372,8 @@ int attention_launch(const T* qkv, int ld, T* out, int ld_out, int batch, int to
         HMV_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         cfg = smem;
     }
-    attention_kernel<T><<<dim3(batch, heads), 256, smem, s>>>(qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq,
-                                                             kv_row0, nk, heads, scale);
+    HMV_CUDA(launch_kernel(attention_kernel<T>, dim3(batch, heads), dim3(256), smem, s, qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq,
+                                                             kv_row0, nk, heads, scale));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -413,6 +419,7 @@ __device__ __forceinline__ void att_load_tile(bf16* dst, const bf16* src, int ld
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out, int ld_out, int tokens_per_sample,
                      int q_row0, int nq, int kv_row0, int nk, int heads, float scale_log2e) {
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t att_smem[];
     bf16* qs = reinterpret_cast<bf16*>(att_smem);
     bf16* ks = qs + kAttQ * kAttPitch;
@@ -532,8 +539,7 @@ int attention_mma_launch(const bf16* qkv, int ld, bf16* out, int ld_out, int bat
         HMV_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    attention_mma_kernel<<<dim3(batch, heads, (nq + kAttQ - 1) / kAttQ), 128, smem, s>>>(
-        qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq, kv_row0, nk, heads, scale * 1.4426950408889634f);
+    HMV_CUDA(launch_kernel(attention_mma_kernel, dim3(batch, heads, (nq + kAttQ - 1) / kAttQ), dim3(128), smem, s, qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq, kv_row0, nk, heads, scale * 1.4426950408889634f));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -546,6 +552,7 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int ld_in, const 
                                  const float* __restrict__ b1, float* __restrict__ out_f32, int ld_out,
                                  const float* __restrict__ g2, const float* __restrict__ b2, T* __restrict__ out_lp,
                                  int ld_lp, int rows, int d, float eps) {
+    pdl_wait();
     constexpr int MAXPER = 20;                 // d <= 640
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -610,7 +617,7 @@ int layernorm_launch(const float* in, int ld_in, const float* g1, const float* b
                      cudaStream_t s) {
     if (rows == 0) return 0;
     HMV_CHECK(d <= 640, "layernorm: d_model > 640 not supported");
-    layernorm_kernel<T><<<(rows + 7) / 8, 256, 0, s>>>(in, ld_in, g1, b1, out_f32, ld_out, g2, b2, out_lp, ld_lp, rows, d, eps);
+    HMV_CUDA(launch_kernel(layernorm_kernel<T>, dim3((rows + 7) / 8), dim3(256), 0, s, in, ld_in, g1, b1, out_f32, ld_out, g2, b2, out_lp, ld_lp, rows, d, eps));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -706,6 +713,7 @@ __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[
 
 __global__ void __launch_bounds__(256)
 gcn_l1_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
+    pdl_wait();
     extern __shared__ __align__(16) float gsm[];
     float* xt = gsm;                                       // [d_in][24]
     float* basis = xt + static_cast<size_t>(p.d_in) * kGcnPad;
@@ -730,6 +738,7 @@ gcn_l1_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
 
 __global__ void __launch_bounds__(256)
 gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
+    pdl_wait();
     extern __shared__ __align__(16) float gsm[];
     float* xt = gsm;                                       // [256][24]
     float* basis = xt + 256 * kGcnPad;
@@ -771,9 +780,9 @@ int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
         HMV_CUDA(cudaFuncSetAttribute(gcn_l23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
         configured = smem;
     }
-    gcn_l1_kernel<<<dim3(p.batch, 256 / kGcnCols), 256, smem, s>>>(p, h1_scratch);
+    HMV_CUDA(launch_kernel(gcn_l1_kernel, dim3(p.batch, 256 / kGcnCols), dim3(256), smem, s, p, h1_scratch));
     HMV_CUDA(cudaGetLastError());
-    gcn_l23_kernel<<<p.batch, 256, smem2, s>>>(p, h1_scratch);
+    HMV_CUDA(launch_kernel(gcn_l23_kernel, dim3(p.batch), dim3(256), smem2, s, p, h1_scratch));
     HMV_CUDA(cudaGetLastError());
     return 0;
 }

@@ -2,6 +2,7 @@
 // Reference behaviour being replaced: src/models/handmvnet.py:158-266 (forward) and the module
 // constructors it relies on (see include/handmvnet_b200.h for the per-entry-point citations).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -17,6 +18,10 @@ namespace hmv {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("HMV_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 // ------------------------------------------------------------------------------------------------
 // layout conversion utilities (stage import/export, unit-test entry point)
@@ -145,6 +150,7 @@ struct hmv_handle {
     struct ProfRec { int layer; int units; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase id, event) recorded while profiling
 };
 
 namespace hmv {
@@ -797,19 +803,35 @@ static int run_gcn(hmv_handle* h, int n, float* out, cudaStream_t s) {
     return gcn_launch(g, h->gcn_h1, s);
 }
 
+static int mark_phase(hmv_handle* h, int id, cudaStream_t s) {
+    if (!h->profiling) return 0;
+    cudaEvent_t e;
+    if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+    else HMV_CUDA(cudaEventCreate(&e));
+    HMV_CUDA(cudaEventRecord(e, s));
+    h->phase_marks.push_back({id, e});
+    return 0;
+}
+
 // front half for one micro-batch of n <= mb samples (pointers already offset): backbone, pose_net, soft-argmax,
 // sampling and token assembly; its tokens land at sample offset `off` of the current fusion pass
 static int run_front(hmv_handle* h, const float* x, const float* bbox, const float* intr, int n, int off, float* heatmap,
                      float* xy_scaled, cudaStream_t s) {
     const int n_img = n * h->V;
+    if (mark_phase(h, 0, s)) return 1;
     if (run_backbone(h, x, n_img, -1, s)) return 1;
+    if (mark_phase(h, 1, s)) return 1;
     if (run_pose(h, n_img, heatmap, xy_scaled, s)) return 1;
-    return h->bf16 ? run_sample_t<bf16>(h, n_img, bbox, intr, s, off) : run_sample_t<float>(h, n_img, bbox, intr, s, off);
+    if (h->bf16 ? run_sample_t<bf16>(h, n_img, bbox, intr, s, off) : run_sample_t<float>(h, n_img, bbox, intr, s, off)) return 1;
+    return mark_phase(h, 2, s);
 }
 // back half for n <= fcap samples: fusion transformer + graph head (small, latency-bound kernels: run once per pass)
 static int run_back(hmv_handle* h, int n, float* joints, cudaStream_t s) {
+    if (mark_phase(h, 3, s)) return 1;
     if (h->bf16 ? run_fusion_t<bf16>(h, n, s) : run_fusion_t<float>(h, n, s)) return 1;
-    return run_gcn(h, n, joints, s);
+    if (mark_phase(h, 4, s)) return 1;
+    if (run_gcn(h, n, joints, s)) return 1;
+    return mark_phase(h, 5, s);
 }
 
 static int check_flag(hmv_handle* h) {
@@ -1255,6 +1277,29 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
     if (tc_flops) *tc_flops = fl;
     if (tc_launches) *tc_launches = static_cast<int64_t>(h->prof.size());
     h->prof.clear();
+    return 0;
+}
+
+/* Stream time (ms, including launch gaps) the profiled passes spent in: [0] backbone, [1] pose_net + soft-argmax +
+ * sampling + token assembly, [2] fusion transformer, [3] graph head.  Resets the marks. */
+int hmv_profile_phases(hmv_handle* h, double* out4) {
+    HMV_CHECK(h && out4, "null argument");
+    HMV_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 4; ++i) out4[i] = 0.0;
+    for (size_t i = 0; i + 1 < h->phase_marks.size(); ++i) {
+        const int a = h->phase_marks[i].first, b = h->phase_marks[i + 1].first;
+        int slot = -1;
+        if (a == 0 && b == 1) slot = 0;
+        else if (a == 1 && b == 2) slot = 1;
+        else if (a == 3 && b == 4) slot = 2;
+        else if (a == 4 && b == 5) slot = 3;
+        if (slot < 0) continue;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->phase_marks[i].second, h->phase_marks[i + 1].second);
+        out4[slot] += t;
+    }
+    for (auto& m : h->phase_marks) h->ev_pool.push_back(m.second);
+    h->phase_marks.clear();
     return 0;
 }
 

@@ -433,5 +433,11 @@ class HandMvNet(nn.Module):
                                                 csv_path.encode() if csv_path else None), "hmv_profile_read")
         return ms.value, fl.value, n.value
 
+    def profile_phases(self):
+        """Stream ms (gaps included) of the profiled passes: backbone, heads, fusion, graph head."""
+        out = (ctypes.c_double * 4)()
+        _lib.check(_lib.load().hmv_profile_phases(self._handle, out), "hmv_profile_phases")
+        return {"backbone": out[0], "heads": out[1], "fusion": out[2], "gcn": out[3]}
+
     def launch_count(self):
         return int(_lib.load().hmv_launch_count(self._handle)) if self._handle is not None else 0

@@ -115,6 +115,8 @@ int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const fl
  * writes one CSV line per launch when csv_path is non-NULL. */
 int hmv_profile_enable(hmv_handle* h, int32_t enable);
 int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc_launches, const char* csv_path);
+/* Stream time (ms, launch gaps included) of the profiled passes per phase: backbone, heads, fusion, graph head. */
+int hmv_profile_phases(hmv_handle* h, double* out4);
 
 /* Number of kernels enqueued by the handle so far (bench.py's gpu_launches claim). */
 int64_t hmv_launch_count(hmv_handle* h);
