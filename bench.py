@@ -43,50 +43,58 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap,utilization.gpu")
+    """SM clock / power / throttle reasons sampled DURING the run through NVML (in-process: an `nvidia-smi -lms`
+    child was measured to stall the GPU for tens of ms per query on this pool, polluting the timed region)."""
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, period_s=0.02):
+        self.rows, self.idx, self.period = [], gpu_index, period_s
+        self._stop = threading.Event()
+        self._thread = None
+        self.error = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            try:
+                return int(ids[self.idx])
+            except (ValueError, IndexError):
+                return self.idx
+        return self.idx
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                time.sleep(self.period)
+            nv.nvmlShutdown()
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons, power = [], 0.0, set(), 0.0
-        for r in self.rows:
-            try:
-                clk, cmax, pw = float(r[1]), float(r[2]), float(r[3])
-            except (ValueError, IndexError):
-                continue
-            mx = max(mx, cmax)
-            power = max(power, pw)
-            try:
-                util = float(r[8])
-            except (ValueError, IndexError):
-                util = 0.0
-            if pw > 250 or util >= 50:         # under load
-                sm.append(clk)
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "power_w_max": power, "samples": len(self.rows), "samples_under_load": len(sm)}
+    def stop(self, t_begin=None, t_end=None):
+        """Summary over the samples taken in [t_begin, t_end] (perf_counter seconds): the timed region."""
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        rows = [r for r in self.rows if (t_begin is None or r[0] >= t_begin) and (t_end is None or r[0] <= t_end)]
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted(name for name, bit in bits.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": getattr(self, "max_sm", None), "reasons": reasons,
+                "power_w_max": max((r[2] for r in rows), default=None), "samples": len(rows),
+                "samples_total": len(self.rows), "source": "NVML, 20 ms period, timed region only", "error": self.error}
 
 
 def cpu_oracle_throughput(batch, iters, warmup, views=5):
@@ -188,6 +196,7 @@ def run_own(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_region0 = time.perf_counter()
     e0.record()
     marks[0].record()
     t_enq = time.perf_counter()
@@ -197,6 +206,7 @@ def run_own(args):
     enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / args.steps
     e1.record()
     barrier()
+    t_region1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1)
     step_ms = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = model.launch_count() - launches0
@@ -224,7 +234,7 @@ def run_own(args):
     tc_ms, tc_flops, tc_n = model.profile_read(csv)
     phases = {k: v / args.steps for k, v in model.profile_phases().items()}
     model.profile(False)
-    clocks = sampler.stop() if rank == 0 else None      # samples cover warm-up, timed, e2e and profiling passes
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 and not args.no_clocks else None
 
     times = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
