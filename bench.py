@@ -69,9 +69,13 @@ class ClockSampler:
             h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
             self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mode = os.environ.get("HMV_BENCH_SAMPLER", "full")
             while not self._stop.is_set():
-                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                t = time.perf_counter()
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0 if mode != "clock" else 0.0
+                rs = int(get_reasons(h)) if mode != "clock" else 0
+                self.rows.append((t, clk, pw, rs, time.perf_counter() - t))
                 time.sleep(self.period)
             nv.nvmlShutdown()
         except Exception as e:  # noqa: BLE001
@@ -94,7 +98,8 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
                 "sm_max_mhz": getattr(self, "max_sm", None), "reasons": reasons,
                 "power_w_max": max((r[2] for r in rows), default=None), "samples": len(rows),
-                "samples_total": len(self.rows), "source": "NVML, 20 ms period, timed region only", "error": self.error}
+                "samples_total": len(self.rows), "query_ms_max": max((r[4] for r in self.rows), default=0.0) * 1e3,
+                "source": f"NVML, {self.period * 1e3:.0f} ms period, timed region only", "error": self.error}
 
 
 def cpu_oracle_throughput(batch, iters, warmup, views=5):
@@ -116,7 +121,7 @@ def cpu_oracle_throughput(batch, iters, warmup, views=5):
     return batch * len(times) / total, total / len(times) * 1e3, torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, lines):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -133,10 +138,10 @@ def run_reference(args):
         "e2e": {"value": ps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    lines.append(json.dumps(line))
 
 
-def run_own(args):
+def run_own(args, lines):
     import torch
     import torch.distributed as dist
     from handmvnet_b200 import HandMvNet
@@ -180,7 +185,7 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period_s=float(os.environ.get("HMV_BENCH_SAMPLER_PERIOD", "0.02")))
     if rank == 0 and not args.no_clocks:
         sampler.start()
     # clock ramp: a GPU coming out of idle needs ~1 s of load before it holds its boost clocks; this pre-warm is
@@ -274,7 +279,7 @@ def run_own(args):
             line["cpu_baseline"] = {"value": ps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "oracle/handmvnet_oracle.py forward, B=1 x 12 steps (+3 warm-up), fp32, all host threads",
                                     "ms_per_forward": ms}
-        print(json.dumps(line), flush=True)
+        lines.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -292,10 +297,23 @@ def main():
     ap.add_argument("--ramp-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_own(args)
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are pointed at stderr
+    # for the duration of the run and the real stdout is restored for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    try:
+        if args.impl == "reference":
+            run_reference(args, lines)
+        else:
+            run_own(args, lines)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":
