@@ -19,6 +19,11 @@ int conv_f32_launch(const ConvF32Params& p, cudaStream_t stream);
 template <typename T>
 int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, int Wp, int pad, cudaStream_t s);
 
+// Fused bf16 stem: conv7x7/2 + BN + ReLU + maxpool3x3/2 straight from fp32 NCHW input (stem_pool.cu).
+// wpack: [7 taps][4 K-chunks][64 couts][8] bf16, element e of chunk kc = (pixel 2*kc + e/4, channel e%4).
+int stem_pool_launch(const float* x, const bf16* wpack, const float* bias, bf16* out, int n_img, int num_sms, int* err_flag,
+                     cudaStream_t s);
+
 // 3x3 / stride 2 / pad 1 max pooling, NHWC (reference resnet.py:165,221).
 template <typename T>
 int maxpool_launch(const T* in, T* out, int n_img, int Hin, int Win, int C, cudaStream_t s);

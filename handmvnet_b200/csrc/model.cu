@@ -89,7 +89,7 @@ struct HostTensor {
     std::vector<int64_t> dims;
 };
 
-enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2 };
+enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3 };
 struct Step {
     int kind;
     std::string name;
@@ -134,6 +134,8 @@ struct hmv_handle {
     float* fused_f32 = nullptr;                   // final fusion output (one of tokA/tokB)
     float* joints_int = nullptr;
     float* gcn_h1 = nullptr;
+    void* stem_w = nullptr;                       // fused stem (bf16 path): packed weights + folded-BN bias
+    float* stem_b = nullptr;
     float* gcn_w[3] = {nullptr, nullptr, nullptr};
     float* gcn_b[3] = {nullptr, nullptr, nullptr};
     float *bbox_int = nullptr, *intr_int = nullptr;
@@ -483,16 +485,33 @@ static int add_gemm_step(hmv_handle* h, const std::string& name, int layer, void
 static int build_backbone(hmv_handle* h) {
     const size_t e = h->esz;
     const size_t act_bytes = static_cast<size_t>(h->mb_img) * 64 * 64 * 256 * e;      // largest activation
-    const int Hp = h->img + 6, Wp = h->img + 16;                                       // 262 x 272
-    if (dev_alloc(h, &h->xpad, static_cast<size_t>(h->mb_img) * Hp * Wp * 4 * e)) return 1;
     if (dev_alloc(h, &h->bufX, act_bytes) || dev_alloc(h, &h->bufY, act_bytes) || dev_alloc(h, &h->bufT1, act_bytes) ||
         dev_alloc(h, &h->bufT2, act_bytes) || dev_alloc(h, &h->bufDS, act_bytes))
         return 1;
+    if (h->bf16) {
+        // ---- fused stem: conv 7x7/2 + BN + ReLU + maxpool 3x3/2 in one kernel (stem_pool.cu) ----
+        std::vector<float> wf, bf;
+        if (fold_conv(h, "backbone.conv1", "backbone.bn1", false, 64, 3, 7, wf, bf)) return 1;
+        std::vector<float> wp(static_cast<size_t>(7) * 4 * 64 * 8, 0.f);
+        for (int r = 0; r < 7; ++r)
+            for (int kc = 0; kc < 4; ++kc)
+                for (int co = 0; co < 64; ++co)
+                    for (int e2 = 0; e2 < 8; ++e2) {
+                        const int sx = 2 * kc + (e2 >> 2), c = e2 & 3;
+                        if (sx < 7 && c < 3)
+                            wp[((static_cast<size_t>(r) * 4 + kc) * 64 + co) * 8 + e2] = wf[(static_cast<size_t>(co) * 49 + r * 7 + sx) * 3 + c];
+                    }
+        if (upload_weights(h, &h->stem_w, wp) || upload_f32(h, &h->stem_b, bf)) return 1;
+        Step st; st.kind = SK_STEM_POOL; st.name = "maxpool"; st.out = h->bufX; st.C = 64; st.H = h->img / 4; st.W = h->img / 4;
+        h->backbone.push_back(st);
+    } else {
+    const int Hp = h->img + 6, Wp = h->img + 16;                                       // 262 x 272
+    if (dev_alloc(h, &h->xpad, static_cast<size_t>(h->mb_img) * Hp * Wp * 4 * e)) return 1;
 
     Step pk; pk.kind = SK_PACK; pk.name = "pack_input"; pk.out = h->xpad; pk.C = 4; pk.H = Hp; pk.W = Wp;
     h->backbone.push_back(pk);
 
-    // ---- stem: conv 7x7/2 + BN + ReLU (resnet.py:218-220) ----
+    // ---- stem: conv 7x7/2 + BN + ReLU (resnet.py:218-220), fp32 check mode ----
     {
         Layer L;
         L.name = "conv1"; L.kind = LK_STEM;
@@ -502,31 +521,21 @@ static int build_backbone(hmv_handle* h) {
         std::vector<float> wf, bf;
         if (fold_conv(h, "backbone.conv1", "backbone.bn1", false, 64, 3, 7, wf, bf)) return 1;
         std::vector<float> wm;
-        if (h->bf16) {           // K = 7 rows x (16 px x 4 ch); px >= 7 and ch 3 are zero
-            L.K = 7 * 64;
-            wm.assign(static_cast<size_t>(64) * L.K, 0.f);
-            for (int co = 0; co < 64; ++co)
-                for (int r = 0; r < 7; ++r)
-                    for (int s = 0; s < 7; ++s)
-                        for (int c = 0; c < 3; ++c)
-                            wm[static_cast<size_t>(co) * L.K + r * 64 + s * 4 + c] = wf[(static_cast<size_t>(co) * 49 + r * 7 + s) * 3 + c];
-        } else {                 // K = 7 x 7 x 4
-            L.K = 49 * 4;
-            wm.assign(static_cast<size_t>(64) * L.K, 0.f);
-            for (int co = 0; co < 64; ++co)
-                for (int t = 0; t < 49; ++t)
-                    for (int c = 0; c < 3; ++c) wm[static_cast<size_t>(co) * L.K + t * 4 + c] = wf[(static_cast<size_t>(co) * 49 + t) * 3 + c];
-        }
+        L.K = 49 * 4;            // K = 7 x 7 x 4 (channel 3 is zero)
+        wm.assign(static_cast<size_t>(64) * L.K, 0.f);
+        for (int co = 0; co < 64; ++co)
+            for (int t = 0; t < 49; ++t)
+                for (int c = 0; c < 3; ++c) wm[static_cast<size_t>(co) * L.K + t * 4 + c] = wf[(static_cast<size_t>(co) * 49 + t) * 3 + c];
         L.bn = 64; L.n_alloc = 64;
-        L.ep = make_ep(h->bufT1, 64, h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR, ACT_RELU);
+        L.ep = make_ep(h->bufT1, 64, OUT_F32_ROWMAJOR, ACT_RELU);
         if (finish_layer(h, L, wm, bf)) return 1;
-        if (h->bf16 && build_tc(h, L)) return 1;
         h->layers.push_back(L);
         add_gemm_step(h, "conv1", static_cast<int>(h->layers.size()) - 1, h->bufT1, 64, L.hout, L.wout);
     }
     Step mp; mp.kind = SK_MAXPOOL; mp.name = "maxpool"; mp.in = h->bufT1; mp.out = h->bufX; mp.C = 64;
     mp.H = h->img / 4; mp.W = h->img / 4;
     h->backbone.push_back(mp);
+    }
 
     // ---- layer1..3 (resnet.py:124-144, 189-203; paper variant: layer3 stride 1) ----
     void* cur = h->bufX;
@@ -732,6 +741,10 @@ static int run_backbone_t(hmv_handle* h, const float* x, int n_img, int num_step
         if (st.kind == SK_PACK) {
             ++h->launches;
             if (pack_input_launch<T>(x, static_cast<T*>(st.out), n_img, h->img, h->img, st.H, st.W, 3, s)) return 1;
+        } else if (st.kind == SK_STEM_POOL) {
+            ++h->launches;
+            if (stem_pool_launch(x, static_cast<const bf16*>(h->stem_w), h->stem_b, static_cast<bf16*>(st.out), n_img, h->num_sms,
+                                 h->err_flag_dev, s)) return 1;
         } else if (st.kind == SK_MAXPOOL) {
             ++h->launches;
             if (maxpool_launch<T>(static_cast<const T*>(st.in), static_cast<T*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s)) return 1;
@@ -838,8 +851,8 @@ static int check_flag(hmv_handle* h) {
     if (h->err_flag_host && *h->err_flag_host != 0) {
         const int code = *h->err_flag_host;
         *h->err_flag_host = 0;
-        set_error("device pipeline timeout in conv_gemm_tc (role code " + std::to_string(code) +
-                  ": 1=TMA producer, 2=MMA/tmem-empty, 3=MMA/smem-full, 4=epilogue)");
+        set_error("device pipeline timeout (role code " + std::to_string(code) +
+                  ": conv_gemm_tc 1=TMA producer, 2=MMA/tmem-empty, 3=MMA/smem-full, 4=epilogue, 5/6=residual ring; stem_pool 11-14)");
         return 1;
     }
     return 0;
