@@ -1027,8 +1027,13 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
     int chunk = 0;
     for (int p0 = 0; p0 < batch; p0 += h->fcap) {
         const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
-        for (int s0 = p0; s0 < p0 + np; s0 += h->mb, ++chunk) {
-            const int n = p0 + np - s0 < h->mb ? p0 + np - s0 : h->mb;
+        for (int s0 = p0; s0 < p0 + np; ++chunk) {
+            // The first two chunks of a call are smaller (mb/4, 3*mb/4) so that compute starts after a short copy;
+            // afterwards copies of full micro-batches are hidden behind the previous chunk's compute.
+            int cap = h->mb;
+            if (h->mb >= 8 && chunk == 0) cap = h->mb / 4;
+            else if (h->mb >= 8 && chunk == 1) cap = h->mb - h->mb / 4;
+            const int n = p0 + np - s0 < cap ? p0 + np - s0 : cap;
             const int b = chunk & 1;
             if (chunk >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
             HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x + s0 * per_sample_x, per_sample_x * n * sizeof(float), cudaMemcpyHostToDevice, cs));
@@ -1040,6 +1045,7 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
                                h->d_xy + static_cast<size_t>(s0) * h->V * 21 * 2, ks))
                 return 1;
             HMV_CUDA(cudaEventRecord(h->ev_consumed[b], ks));
+            s0 += n;
         }
         if (hmv::run_back(h, np, h->d_j + static_cast<size_t>(p0) * 21 * 3, ks)) return 1;
     }

@@ -64,7 +64,7 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
         reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);          // horizontal padding pixels stay zero
     if (tid == 0) {
         for (int i = 0; i < kRingSlots; ++i) {
-            mbar_init(pfull0 + 8 * i, 4);                  // one arrival per converter warp
+            mbar_init(pfull0 + 8 * i, 1);                  // the converter warp that owns the pair
             mbar_init(pempty0 + 8 * i, 1);                 // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
@@ -91,6 +91,7 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
 
     if (warp < 4) {
         // ===================== converters: fp32 NCHW rows -> bf16 NHWC4 padded rows =====================
+        // Warp w owns every 4th row pair (whole rows: lane -> 8 pixels), so four pairs' global loads are in flight.
         uint32_t gq = 0;                                   // running pair counter (ring position / phase)
         bool alive = true;
         for (int item = blockIdx.x; item < num_items && alive; item += gridDim.x) {
@@ -98,25 +99,39 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
             const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * kStripPool - 1;
             const float* xn = x + static_cast<size_t>(n) * 3 * kImg * kImg;
             for (int j = c_lo; j <= c_hi + 3 && alive; ++j, ++gq) {              // pair j = padded rows 2j, 2j+1
+                if ((gq & 3) != static_cast<uint32_t>(warp)) continue;
                 const uint32_t slot = gq % kRingSlots;
+                float4 v[2][3][2];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = 2 * j + rr - 3;                              // original input row
+                    const bool ok = row >= 0 && row < kImg;
+                    const float* pr = xn + static_cast<size_t>(ok ? row : 0) * kImg + 8 * lane;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                        for (int hq = 0; hq < 2; ++hq)
+                            v[rr][ch][hq] = ok ? __ldg(reinterpret_cast<const float4*>(pr + ch * kImg * kImg) + hq)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (!mbar_wait(pempty0 + 8 * slot, ((gq / kRingSlots) & 1) ^ 1, err_flag, 11)) { alive = false; break; }
                 uint8_t* dst = ring + slot * kPairBytes;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const int row = 2 * j + rr - 3;                              // original input row
-                    float2 v0 = make_float2(0.f, 0.f), v1 = v0, v2 = v0;
-                    if (row >= 0 && row < kImg) {                                // thread tid -> pixels 2*tid, 2*tid+1
-                        const float* pr = xn + static_cast<size_t>(row) * kImg + 2 * tid;
-                        v0 = __ldg(reinterpret_cast<const float2*>(pr));
-                        v1 = __ldg(reinterpret_cast<const float2*>(pr + kImg * kImg));
-                        v2 = __ldg(reinterpret_cast<const float2*>(pr + 2 * kImg * kImg));
+                    uint2* d = reinterpret_cast<uint2*>(dst + rr * kRowPitch + (8 * lane + 3) * 8);   // +3: left padding
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const float c0[4] = {v[rr][0][hq].x, v[rr][0][hq].y, v[rr][0][hq].z, v[rr][0][hq].w};
+                        const float c1[4] = {v[rr][1][hq].x, v[rr][1][hq].y, v[rr][1][hq].z, v[rr][1][hq].w};
+                        const float c2[4] = {v[rr][2][hq].x, v[rr][2][hq].y, v[rr][2][hq].z, v[rr][2][hq].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint2 o;
+                            o.x = pack_bf16x2(c0[e], c1[e]);
+                            o.y = pack_bf16x2(c2[e], 0.f);
+                            d[hq * 4 + e] = o;
+                        }
                     }
-                    uint2 a, b;
-                    a.x = pack_bf16x2(v0.x, v1.x); a.y = pack_bf16x2(v2.x, 0.f);
-                    b.x = pack_bf16x2(v0.y, v1.y); b.y = pack_bf16x2(v2.y, 0.f);
-                    uint2* d = reinterpret_cast<uint2*>(dst + rr * kRowPitch + (2 * tid + 3) * 8);   // +3: left padding
-                    d[0] = a;
-                    d[1] = b;
                 }
                 fence_async_smem();                        // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
