@@ -28,8 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "multi-view hand poses/sec (HandMvNet forward, HO3D release config, 5 views)"
+METRIC_FMT = "multi-view hand poses/sec (HandMvNet forward, release config, {v} views)"
 UNIT = "poses/s"
 FLOP_PER_SAMPLE_V5 = 108.515e9        # SURVEY.md §8d (FlopCounterMode over the reference forward)
+FLOP_PER_SAMPLE = {5: 108.515e9, 8: 173.58e9}
 
 
 def load_peaks():
@@ -155,7 +157,7 @@ def run_own(args, lines):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    views, B = 5, args.batch
+    views, B = args.views, args.batch
     cfg = release_config(views, True)
     torch.manual_seed(0)
     model = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision="bf16", micro_batch=args.micro_batch)
@@ -164,13 +166,19 @@ def run_own(args, lines):
     model.prepare(dev)
 
     g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, views, 3, 256, 256, generator=g).pin_memory()            # 251 MB at B=64 (> 126 MB L2)
     c = torch.rand(B, views, 2, generator=g) * torch.tensor([320.0, 240.0]) + torch.tensor([160.0, 120.0])
     side = 100 + 150 * torch.rand(B, views, 1, generator=g)
     bbox_host = torch.cat([c - side / 2, c + side / 2], dim=-1).pin_memory()
     f = 500 + 200 * torch.rand(B, views, 1, generator=g)
     intr_host = torch.cat([f, f, torch.full((B, views, 1), 320.0), torch.full((B, views, 1), 240.0)], dim=-1).pin_memory()
-    x, bbox, intr = x_host.to(dev), bbox_host.to(dev), intr_host.to(dev)
+    if args.no_e2e:                                    # large-batch sweeps: inputs are generated on the device
+        gd = torch.Generator(device=dev).manual_seed(1234 + rank)
+        x_host = None
+        x = torch.randn(B, views, 3, 256, 256, device=dev, generator=gd)
+    else:
+        x_host = torch.randn(B, views, 3, 256, 256, generator=g).pin_memory()        # 251 MB at B=64 (> 126 MB L2)
+        x = x_host.to(dev)
+    bbox, intr = bbox_host.to(dev), intr_host.to(dev)
     cam = {"intrinsic": intr}
     gathered = [torch.empty(B, 21, 3, device=dev) for _ in range(world)] if world > 1 else None
 
@@ -218,18 +226,21 @@ def run_own(args, lines):
     assert torch.isfinite(out["joints_cam"]).all()
 
     # ---- end to end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
-    cam_host = {"intrinsic": intr_host}
-    for _ in range(max(1, args.warmup // 2)):
-        model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ho = model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    h2d = x_host.numel() * 4 + bbox_host.numel() * 4 + intr_host.numel() * 4
-    d2h = ho["joints_cam"].numel() * 4 + ho["joints_crop_img"].numel() * 4
+    h2d = x.numel() * 4 + bbox_host.numel() * 4 + intr_host.numel() * 4
+    d2h = B * 21 * 3 * 4 + B * views * 21 * 2 * 4
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        cam_host = {"intrinsic": intr_host}
+        for _ in range(max(1, args.warmup // 2)):
+            model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ho = model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        d2h = ho["joints_cam"].numel() * 4 + ho["joints_crop_img"].numel() * 4
 
     # ---- per-launch timing of the dominant kernel: same steps again with CUDA events around every launch ----
     model.profile(True)
@@ -241,7 +252,7 @@ def run_own(args, lines):
     model.profile(False)
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 and not args.no_clocks else None
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    times = torch.tensor([dev_ms, 0.0 if args.no_e2e else e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
@@ -250,19 +261,20 @@ def run_own(args, lines):
         value = B * world * args.steps / (dev_ms * 1e-3)
         achieved = tc_flops / (tc_ms * 1e-3) * 1e-12 if tc_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if views == 5 else METRIC_FMT.format(v=views), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps,
             "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"HO3D_HandMvNet release config, synthetic 5-view B={B} per GPU, bf16, random-init weights",
+            "config": {"workload": f"{'HO3D' if views == 5 else 'DexYCB-style'}_HandMvNet release config, synthetic {views}-view B={B} per GPU, bf16, random-init weights",
                        "views": views, "image": 256, "batch_per_gpu": B, "micro_batch": args.micro_batch,
                        "parallelism": f"batch-sharded x{world} (replicated weights, NCCL all-gather of poses)",
                        "l2": f"inputs {x.numel() * 4 / 2**20:.0f} MiB + {0.445 * B:.1f} GB of activations per step exceed the 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "api": "HandMvNet.forward_host -> hmv_forward_host (pinned host buffers; poses copied back)"},
+            "e2e": None if args.no_e2e else {
+                "value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "HandMvNet.forward_host -> hmv_forward_host (pinned host buffers; poses copied back)"},
             "gpu_launches": launches,
             "roofline": {"kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -271,7 +283,7 @@ def run_own(args, lines):
                          "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps,
                          "kernel_share_of_step": (tc_ms / args.steps) / (dev_ms / args.steps),
                          "timing": "second pass over the same steps with CUDA events around every launch",
-                         "end_to_end_model_tflops": FLOP_PER_SAMPLE_V5 * value / world * 1e-12,
+                         "end_to_end_model_tflops": FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9) * value / world * 1e-12,
                          "phase_ms_per_step": phases},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -293,7 +305,9 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=16, help="samples per internal pass")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi clock sampler")
+    ap.add_argument("--views", type=int, default=5, help="camera views per sample (5 = HO3D release config, 8 = DexYCB)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large-batch sweeps)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not run the NVML clock sampler")
     ap.add_argument("--ramp-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

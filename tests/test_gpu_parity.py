@@ -271,3 +271,45 @@ def test_known_answers_on_device():
     assert rel_l2(tok[0, :, :512], want.reshape(105, 512)) < 1e-4
     assert torch.allclose(tok[0, :, 512:514], exp.reshape(105, 2), atol=1e-4)
     assert torch.allclose(tok[0, :, 514:], O.crop_fov(bbox, intr).repeat_interleave(21, 0), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel-level cases the whole-model tests do not reach
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("views", [2, 4, 16])
+def test_fusion_stage_view_sweep(views):
+    """Fusion transformer alone for 42 / 84 / 336 tokens (BASELINE.json config 5): the flash-style attention kernel
+    crosses its 64-key block boundary several times at 16 views; cross layer has 21 queries vs 21*(V-1) keys."""
+    b = 2
+    m, ocfg, sd = build_pair(views, True, "bf16", micro_batch=b, seed=11)
+    g = torch.Generator().manual_seed(views)
+    tok = torch.randn(b, 21 * views, 524, generator=g) * 2.0
+    ref = O.fusion(sd, tok, 5, add_pos=False, query_len=21)
+    m.tensor_set("tokens", tok.cuda(), b)
+    m.stage_run("fusion", b)
+    err = rel_l2(m.tensor_get("fused", b), ref)
+    m.synchronize()
+    assert err < TOL["bf16"], f"V={views}: fused rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("n_img", [1, 3, 7])
+def test_fused_stem_kernel(n_img):
+    """conv7x7/2 + BN + ReLU + maxpool3x3/2 fused kernel against the oracle's max-pool output, including image
+    borders (zero padding of the conv, implicit -inf padding of the pool) and strip boundaries inside an image."""
+    m, ocfg, sd = build_pair(5, True, "bf16", micro_batch=2, seed=4)
+    g = torch.Generator().manual_seed(n_img)
+    x = torch.randn(n_img, 3, 256, 256, generator=g)
+    x[:, :, :4] += 3.0                      # make the top / bottom / left / right borders matter
+    x[:, :, -4:] -= 3.0
+    x[:, :, :, :4] += 2.0
+    x[:, :, :, -4:] -= 2.0
+    taps = {}
+    O.backbone(sd, x, taps)
+    names = m.debug_backbone_steps()
+    assert names[0] == "maxpool"
+    out = m.debug_backbone(x.cuda(), 1).cpu()
+    m.synchronize()
+    assert out.shape == taps["maxpool"].shape
+    assert rel_l2(out, taps["maxpool"]) < 5e-3
+    # every strip row and column is covered: no pooled pixel may be left at zero where the oracle is positive
+    assert ((out == 0) & (taps["maxpool"] > 0.05)).float().mean() < 1e-4
