@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=16, help="samples per internal pass")
+    ap.add_argument("--micro-batch", type=int, default=64, help="samples per internal pass")
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--views", type=int, default=5, help="camera views per sample (5 = HO3D release config, 8 = DexYCB)")
