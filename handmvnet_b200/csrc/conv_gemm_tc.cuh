@@ -8,14 +8,15 @@
 //   * A (activations, NHWC bf16) is described by ONE 5-D TMA tensor map
 //     (C, W', A, H', N); a "tap" is a coordinate offset (c_off, dw, a, dh) into that map, so
 //     3x3/pad-1 convs are 9 shifted box loads with hardware zero fill, stride-2 convs address
-//     the input through its (row-parity, col-parity) view, the 7x7/2 stem uses an overlapping
-//     16-byte pixel-pair stride, and 1x1 convs / linears are the single-tap "flat" case.
+//     the input through its (row-parity, col-parity) view, and 1x1 convs / linears are the
+//     single-tap "flat" case (the 7x7/2 stem has its own fused kernel, stem_pool.cu).
 //   * W is [N_alloc, K] K-major bf16 (BN scale folded in), one 2-D tensor map.
 //   * Both land in 128B-swizzled shared memory (4..8 stage mbarrier ring) and feed
 //     tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread; the fp32
 //     accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
 //     tile i+1.  Epilogue warps read TMEM with tcgen05.ld (32 lanes x 32b), add the folded-BN
-//     bias, the optional residual, apply ReLU/GELU and store bf16 NHWC / fp32 / fp32-NCHW.
+//     bias, the optional residual, apply ReLU/GELU and write bf16 NHWC through a swizzled
+//     shared-memory staging ring + TMA stores (or fp32 / fp32-NCHW straight from registers).
 #pragma once
 #include "common.cuh"
 

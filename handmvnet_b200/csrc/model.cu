@@ -147,6 +147,14 @@ struct hmv_handle {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     float *d_bbox = nullptr, *d_intr = nullptr, *d_hm = nullptr, *d_xy = nullptr, *d_j = nullptr;
     int host_cap = 0;
+    // CUDA graphs for small batches (launch-bound regime, B=1 latency): one instantiated graph per batch size over
+    // internal I/O buffers; calls 1 and 2 with a batch size run eagerly / capture, later calls replay.
+    struct GraphSlot { int calls = 0; int kernels = 0; cudaGraphExec_t exec = nullptr; };
+    cudaStream_t graph_stream = nullptr;          // capture / replay stream (the caller's may be the legacy default stream)
+    cudaEvent_t graph_in = nullptr, graph_out = nullptr;
+    std::map<int, GraphSlot> graphs;
+    int graph_max_batch = 0;                      // 0 = disabled
+    float *g_x = nullptr, *g_bbox = nullptr, *g_intr = nullptr, *g_hm = nullptr, *g_xy = nullptr, *g_j = nullptr;
     // optional per-launch profiling of the tensor-core GEMM kernel (bench.py roofline leg)
     bool profiling = false;
     struct ProfRec { int layer; int units; cudaEvent_t e0, e1; };
@@ -305,15 +313,8 @@ static int build_tc(hmv_handle* h, Layer& L) {
                 for (int s = 0; s < 3; ++s)
                     t.p.taps[r * 3 + s] = TcTap{(s == 1 ? 0 : 1) * L.cin, s == 0 ? -1 : 0, r == 1 ? 0 : 1, r == 0 ? -1 : 0};
         }
-    } else {  // LK_STEM: xpad [N, Hp, Wp, 4]; one K block per filter row = 16 pixels x 4 channels
-        const uint64_t Hp = L.hin, Wp = L.win;
-        dims[0] = 64; dims[1] = L.wout; dims[2] = 2; dims[3] = Hp / 2; dims[4] = N;
-        strides[0] = 16; strides[1] = Wp * 8; strides[2] = 2 * Wp * 8; strides[3] = Hp * Wp * 8;
-        box[0] = 64; box[1] = 128; box[2] = box[3] = box[4] = 1;
-        HMV_CHECK(L.wout == 128, "stem: output width must be 128");
-        t.p.flat = 0; t.p.hbox = 1; t.p.tpi = L.hout;
-        t.p.num_taps = 7; t.p.cblks = 1;
-        for (int r = 0; r < 7; ++r) t.p.taps[r] = TcTap{0, 0, r & 1, r >> 1};
+    } else {
+        HMV_CHECK(false, "the 7x7 stem has its own fused kernel on the tensor-core path (stem_pool.cu)");
     }
     if (tc_make_tmap_act(&t.tmA, L.in, dims, strides, box)) {
         set_error(std::string(get_error()) + " [A map of " + L.name + "]");
@@ -922,6 +923,10 @@ int hmv_destroy(hmv_handle* h) {
     if (h->d_j) cudaFree(h->d_j);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+    if (h->graph_in) cudaEventDestroy(h->graph_in);
+    if (h->graph_out) cudaEventDestroy(h->graph_out);
     for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
@@ -946,20 +951,30 @@ int hmv_prepare(hmv_handle* h) {
     HMV_CUDA(cudaSetDevice(h->cfg.device));
     if (hmv::build_backbone(h)) return 1;
     if (hmv::build_heads(h)) return 1;
+    {   // small-batch CUDA-graph path (HMV_NO_GRAPH=1 disables it)
+        const char* e = getenv("HMV_NO_GRAPH");
+        h->graph_max_batch = (e && e[0] == '1') ? 0 : (h->mb < 8 ? h->mb : 8);
+        if (h->graph_max_batch > 0) {
+            const size_t nimg = static_cast<size_t>(h->graph_max_batch) * h->V;
+            if (hmv::dev_alloc_t(h, &h->g_x, nimg * 3 * h->img * h->img * sizeof(float), false) ||
+                hmv::dev_alloc_t(h, &h->g_bbox, nimg * 4 * sizeof(float)) || hmv::dev_alloc_t(h, &h->g_intr, nimg * 4 * sizeof(float)) ||
+                hmv::dev_alloc_t(h, &h->g_hm, nimg * 21 * h->hm * h->hm * sizeof(float)) ||
+                hmv::dev_alloc_t(h, &h->g_xy, nimg * 21 * 2 * sizeof(float)) ||
+                hmv::dev_alloc_t(h, &h->g_j, static_cast<size_t>(h->graph_max_batch) * 21 * 3 * sizeof(float)))
+                return 1;
+            HMV_CUDA(cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+            HMV_CUDA(cudaEventCreateWithFlags(&h->graph_in, cudaEventDisableTiming));
+            HMV_CUDA(cudaEventCreateWithFlags(&h->graph_out, cudaEventDisableTiming));
+        }
+    }
     HMV_CUDA(cudaDeviceSynchronize());
     h->weights.clear();
     h->prepared = true;
     return 0;
 }
 
-int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
-                float* joints_crop_img, float* joints_cam, void* stream) {
-    HMV_CHECK(h && h->prepared, "hmv_forward: handle not prepared");
-    HMV_CHECK(batch >= 0, "negative batch");
-    HMV_CHECK(x || batch == 0, "hmv_forward: x is null");
-    HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
-    if (hmv::check_flag(h)) return 1;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+static int forward_eager(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
+                         float* joints_crop_img, float* joints_cam, cudaStream_t s) {
     const size_t per_sample_x = static_cast<size_t>(h->V) * 3 * h->img * h->img;
     for (int p0 = 0; p0 < batch; p0 += h->fcap) {                     // fusion passes
         const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
@@ -974,6 +989,71 @@ int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* i
         if (hmv::run_back(h, np, joints_cam ? joints_cam + static_cast<size_t>(p0) * 21 * 3 : nullptr, s)) return 1;
     }
     return 0;
+}
+
+// Small batches are launch-bound (88 launches of a few microseconds each): replay them as one CUDA graph over the
+// handle's internal I/O buffers; inputs / outputs are staged with device-to-device copies around the launch.
+static int forward_graph(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
+                         float* joints_crop_img, float* joints_cam, cudaStream_t s) {
+    hmv_handle::GraphSlot& g = h->graphs[batch];
+    if (g.exec == nullptr && g.calls == 0) {          // first call: eager (lazy cudaFuncSetAttribute calls happen here)
+        ++g.calls;
+        return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    }
+    const size_t nimg = static_cast<size_t>(batch) * h->V;
+    const size_t xb = nimg * 3 * h->img * h->img * sizeof(float);
+    cudaStream_t user = s;
+    s = h->graph_stream;                               // everything below runs on the handle's own stream
+    HMV_CUDA(cudaEventRecord(h->graph_in, user));
+    HMV_CUDA(cudaStreamWaitEvent(s, h->graph_in, 0));
+    HMV_CUDA(cudaMemcpyAsync(h->g_x, x, xb, cudaMemcpyDeviceToDevice, s));
+    if (h->cfg.use_crop) {
+        HMV_CUDA(cudaMemcpyAsync(h->g_bbox, bbox, nimg * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        HMV_CUDA(cudaMemcpyAsync(h->g_intr, intr, nimg * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    if (g.exec == nullptr) {
+        cudaGraph_t graph = nullptr;
+        HMV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int64_t launches0 = h->launches;
+        int rc = forward_eager(h, h->g_x, h->cfg.use_crop ? h->g_bbox : nullptr, h->cfg.use_crop ? h->g_intr : nullptr, batch,
+                               h->g_hm, h->g_xy, h->g_j, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        g.kernels = static_cast<int>(h->launches - launches0);
+        h->launches = launches0;
+        if (rc == 0 && ce == cudaSuccess && graph != nullptr) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != 0 || ce != cudaSuccess || g.exec == nullptr) {     // capture unsupported here: eager from now on
+            cudaGetLastError();
+            g.exec = nullptr;
+            h->graph_max_batch = 0;
+            if (rc != 0) return rc;
+            if (forward_eager(h, h->g_x, h->cfg.use_crop ? h->g_bbox : nullptr, h->cfg.use_crop ? h->g_intr : nullptr, batch,
+                              h->g_hm, h->g_xy, h->g_j, s)) return 1;
+        }
+        g.calls = 2;
+    }
+    if (g.exec != nullptr) {
+        HMV_CUDA(cudaGraphLaunch(g.exec, s));
+        h->launches += g.kernels;                      // kernels inside the replayed graph
+    }
+    if (heatmap) HMV_CUDA(cudaMemcpyAsync(heatmap, h->g_hm, nimg * 21 * h->hm * h->hm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (joints_crop_img) HMV_CUDA(cudaMemcpyAsync(joints_crop_img, h->g_xy, nimg * 21 * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (joints_cam) HMV_CUDA(cudaMemcpyAsync(joints_cam, h->g_j, static_cast<size_t>(batch) * 21 * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    HMV_CUDA(cudaEventRecord(h->graph_out, s));
+    HMV_CUDA(cudaStreamWaitEvent(user, h->graph_out, 0));
+    return 0;
+}
+
+int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
+                float* joints_crop_img, float* joints_cam, void* stream) {
+    HMV_CHECK(h && h->prepared, "hmv_forward: handle not prepared");
+    HMV_CHECK(batch >= 0, "negative batch");
+    HMV_CHECK(x || batch == 0, "hmv_forward: x is null");
+    HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
+    if (hmv::check_flag(h)) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (batch > 0 && batch <= h->graph_max_batch && !h->profiling) return forward_graph(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
 }
 
 int hmv_synchronize(hmv_handle* h) {

@@ -143,14 +143,6 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, bool relu) {
 __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 
 // K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices; `lbo` = byte distance between the two 16-byte
