@@ -1,0 +1,429 @@
+// Fused bottleneck tail for sm_100a: conv3x3(+BN+ReLU) -> conv1x1(+BN) + residual + ReLU in ONE persistent
+// tcgen05 kernel (reference: backbones/resnet.py:131-143, `conv2/bn2/relu/conv3/bn3/+=identity/relu`).
+//
+// Why: conv2 (K = 9*P) is tensor-bound and conv3 (K = P, 4*P outputs + a 4*P-wide residual) is HBM-bound; as two
+// kernels their times add.  Here one CTA owns an M tile (128 pixels) for BOTH GEMMs and interleaves them, so the
+// residual reads / output stores of conv3 stream while the tensor pipe works on the next tile's conv2:
+//
+//   MMA issue order of a CTA (tiles m_0, m_1, ... strided by the grid):
+//     T2(m_0) | T2(m_1) | T2(m_2) with T3(m_0, chunk c) slotted in after every 4th K block | T2(m_3) with T3(m_1, .) | ... | T3 tails
+//   (conv3 lags conv2 by two tiles so that the Y2 round trip below is never on the critical path)
+//   T2(m):    acc1[128 x P]    = A_3x3[m] * W2^T          (K = 9*P, same TMA tap addressing as conv_gemm_tc.cu)
+//   T3(m, c): acc2[128 x 128]  = Y2[m]    * W3[c]^T       (K = P; c = one of P/32 column chunks of the 4*P outputs)
+//   Y2[m] (conv2 output, bf16, bias+ReLU applied) is written to global by this CTA's epilogue with TMA stores and read
+//   back through TMA as the A operand of T3 (it never leaves L2); an mbarrier orders the store completion before
+//   the reload.  TMEM: acc1 at column 0 (double-buffered at 0 / P when P <= 128), acc2 double-buffered at columns
+//   256/384.  Epilogue order mirrors the MMA order: E3(m_{i-2}, all chunks) then E2(m_i).
+//
+// Shared memory: kStages operand stages (A 16 KiB + B max(P*128, 16 KiB)) and ONE ring of 4 chunk slots
+// (128 rows x 64 bf16, 128B swizzle) that serves both as residual landing zone (TMA load by warp 2) and as store
+// staging (the epilogue adds bias/residual in place, then TMA-stores the slot).
+#include "conv_gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace hmv {
+
+namespace {
+
+constexpr int kBtSlots = 4;
+constexpr int kBtChunkCols = 64;
+constexpr int kBtChunkBytes = kTcBlockM * kBtChunkCols * 2;     // 16 KiB
+constexpr int kBtAcc2Col = 256;                                 // TMEM column of the first conv3 accumulator
+constexpr int kBtN3 = 128;                                      // conv3 chunk width
+constexpr int kBtLag = 2;                                       // conv3 of tile i-kBtLag runs inside the K loop of tile i
+
+template <int P>
+struct BtCfg {
+    static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;                  // 16 KiB
+    static constexpr int kB2Bytes = P * kTcBlockK * 2;
+    static constexpr int kB3Bytes = kBtN3 * kTcBlockK * 2;                     // 16 KiB
+    static constexpr int kBSlot = kB2Bytes > kB3Bytes ? kB2Bytes : kB3Bytes;
+    static constexpr int kStageBytes = kABytes + kBSlot;
+    static constexpr int kStagesRaw = (226 * 1024 - kBtSlots * kBtChunkBytes - 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kKB2 = 9 * P / kTcBlockK;                             // K blocks of conv2
+    static constexpr int kKB3 = P / kTcBlockK;                                 // K blocks of one conv3 chunk
+    static constexpr int kNCH = 4 * P / kBtN3;                                 // conv3 chunks per tile
+    static constexpr int kNA = P <= 128 ? 2 : 1;                               // conv2 accumulators in TMEM (columns 0 / P)
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBtSlots * kBtChunkBytes + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(P == 64 || P == 128 || P == 256, "bottleneck widths of ResNet-50");
+    static_assert(kStages >= 3 && kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(kKB2 / 4 >= kNCH, "every conv3 chunk of the previous tile fits between the K blocks of conv2");
+};
+
+// Segment i of a CTA: the K loop of conv2 on its i-th tile (if any) with the conv3 chunks of tile i-1 (if any) slotted in
+// after every 4th K block; whatever is left (the tail segment has no K loop) follows.  The TMA producer and the MMA
+// issuer walk the same schedule.
+template <int P, typename F2, typename F3>
+__device__ __forceinline__ bool bt_segment(bool has_t2, bool has_t3, F2&& kblock2, F3&& chunk3) {
+    const int nkb = has_t2 ? BtCfg<P>::kKB2 : 0;
+    const int nch = has_t3 ? BtCfg<P>::kNCH : 0;
+    int c = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+        if (!kblock2(kb)) return false;
+        if ((kb & 3) == 3 && c < nch) {
+            if (!chunk3(c)) return false;
+            ++c;
+        }
+    }
+    for (; c < nch; ++c)
+        if (!chunk3(c)) return false;
+    return true;
+}
+
+// mbar_wait that also accumulates the stall time (clock cycles) into `acc` -- read back by HMV_BT_PROF=1 runs
+__device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* err_flag, int code, long long& acc) {
+    const long long t0 = clock64();                  // (try_wait may suspend inside the instruction: time it as well)
+    const bool ok = mbar_wait(bar, parity, err_flag, code);
+    acc += clock64() - t0;
+    return ok;
+}
+
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int P>
+__global__ void __launch_bounds__(kTcThreads, 1)
+bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 input, 5-D activation map
+                       const __grid_constant__ CUtensorMap tmW2,   // [P, 9P] box {64, P}
+                       const __grid_constant__ CUtensorMap tmY2s,  // conv2 output [rows, P], store box {64, 32}
+                       const __grid_constant__ CUtensorMap tmY2l,  // conv2 output [rows, P], load box {64, 128}
+                       const __grid_constant__ CUtensorMap tmW3,   // [4P, P] box {64, 128}
+                       const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 4P], store box {64, 32}
+                       const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 4P], load box {64, 128}
+                       const __grid_constant__ BtParams p) {
+    using Cfg = BtCfg<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* slots = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slots + kBtSlots * kBtChunkBytes);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * Cfg::kStages;
+    const uint32_t t1full0 = empty0 + 8 * Cfg::kStages;
+    const uint32_t t1empty0 = t1full0 + 16;
+    const uint32_t t2full0 = t1empty0 + 16;
+    const uint32_t t2empty0 = t2full0 + 16;
+    const uint32_t cfull0 = t2empty0 + 16;
+    const uint32_t cempty0 = cfull0 + 8 * kBtSlots;
+    const uint32_t y2ready0 = cempty0 + 8 * kBtSlots;       // two barriers: even / odd tiles of this CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 8 + 2 * kBtSlots + 2);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t slots_base = smem_u32(slots);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmW2); prefetch_tmap(&tmY2s); prefetch_tmap(&tmY2l);
+        prefetch_tmap(&tmW3); prefetch_tmap(&tmOut); prefetch_tmap(&tmRes);
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(t1full0 + 8 * i, 1);
+            mbar_init(t1empty0 + 8 * i, 8);                 // one arrival per epilogue warp
+            mbar_init(t2full0 + 8 * i, 1);
+            mbar_init(t2empty0 + 8 * i, 8);
+            mbar_init(y2ready0 + 8 * i, 4);
+        }
+        for (int i = 0; i < kBtSlots; ++i) {
+            mbar_init(cfull0 + 8 * i, 1);
+            mbar_init(cempty0 + 8 * i, 4);                  // the four slab-store issuers
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();
+    pdl_launch_dependents();
+
+    const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+
+    if (warp == 0) {
+        // ===================== TMA producer of the operand ring =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            long long w_empty = 0, w_y2 = 0;
+            for (int i = 0; i < n_i + kBtLag; ++i) {
+                const int j3 = i - kBtLag;                   // index of the tile whose conv3 runs in this segment
+                const int m2 = tile_of(i), m3 = tile_of(j3);
+                const int h0 = (m2 % p.tpi) * p.hbox, img = m2 / p.tpi;
+                const bool ok = bt_segment<P>(i < n_i, j3 >= 0,
+                    [&](int kb) {
+                        if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 21, w_empty)) return false;
+                        const TcTap tap = p.taps[kb / p.cblks];
+                        const int cb = kb % p.cblks;
+                        const uint32_t fb = full0 + 8 * stage;
+                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                        mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB2Bytes);
+                        tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
+                        tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        return true;
+                    },
+                    [&](int c) {
+                        // Y2[m3] was TMA-stored by this CTA's epilogue; wait until those stores have completed
+                        if (c == 0 && !timed_wait(y2ready0 + 8 * (j3 & 1), static_cast<uint32_t>(j3 >> 1) & 1u, p.err_flag, 22, w_y2)) return false;
+                        if (c == 0) fence_proxy_async_all();
+                        for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
+                            if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 23, w_empty)) return false;
+                            const uint32_t fb = full0 + 8 * stage;
+                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                            mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
+                            tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
+                            tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        }
+                        return true;
+                    });
+                if (!ok) break;
+            }
+            if (p.prof) { p.prof[blockIdx.x * 16 + 5] = w_empty; p.prof[blockIdx.x * 16 + 6] = w_y2; }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc2 = make_idesc(P);
+            constexpr uint32_t idesc3 = make_idesc(kBtN3);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t q = 0;                                  // running conv3 chunk counter (TMEM slot = q & 1)
+            long long w_t1e = 0, w_f2 = 0, w_t2e = 0, w_f3 = 0;
+            const long long t_start = clock64();
+            for (int i = 0; i < n_i + kBtLag; ++i) {
+                const uint32_t a = static_cast<uint32_t>(i) % Cfg::kNA, ause = static_cast<uint32_t>(i) / Cfg::kNA;
+                const uint32_t acc1 = tmem_base + a * P;
+                const bool ok = bt_segment<P>(i < n_i, i >= kBtLag,
+                    [&](int kb) {
+                        if (kb == 0) {                       // this conv2 accumulator was drained by the epilogue of its previous tile
+                            if (!timed_wait(t1empty0 + 8 * a, (ause & 1u) ^ 1u, p.err_flag, 24, w_t1e)) return false;
+                            tc_fence_after();
+                        }
+                        if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 25, w_f2)) return false;
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                        for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                            umma_f16(acc1, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc2,
+                                     (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(empty0 + 8 * stage);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
+                        return true;
+                    },
+                    [&](int) {
+                        const uint32_t s = q & 1u, use = q >> 1;
+                        if (!timed_wait(t2empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 26, w_t2e)) return false;
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + kBtAcc2Col + s * kBtN3;
+                        for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
+                            if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 27, w_f3)) return false;
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                            const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                                umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
+                                         (kb3 | k) != 0 ? 1u : 0u);
+                            umma_commit(empty0 + 8 * stage);
+                            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(t2full0 + 8 * s);
+                        ++q;
+                        return true;
+                    });
+                if (!ok) break;
+            }
+            if (p.prof) {
+                long long* o = p.prof + blockIdx.x * 16;
+                o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===================== chunk-slot producer: residual prefetch (conv3 chunks) / plain hand-over (conv2 chunks) ============
+        if (lane == 0) {
+            uint32_t g = 0;
+            bool alive = true;
+            long long w_ce = 0;
+            for (int i = 0; i < n_i + kBtLag && alive; ++i) {
+                if (i >= kBtLag) {
+                    const int m3 = tile_of(i - kBtLag);
+                    for (int c = 0; c < Cfg::kNCH * 2 && alive; ++c, ++g) {
+                        const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
+                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 28, w_ce)) { alive = false; break; }
+                        mbar_arrive_expect_tx(cfull0 + 8 * slot, kBtChunkBytes);
+                        tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
+                    }
+                }
+                if (i < n_i) {
+                    for (int c = 0; c < P / kBtChunkCols && alive; ++c, ++g) {
+                        const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
+                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 29, w_ce)) { alive = false; break; }
+                        mbar_arrive(cfull0 + 8 * slot);
+                    }
+                }
+            }
+            if (p.prof) p.prof[blockIdx.x * 16 + 12] = w_ce;
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of a 64-column chunk =====================
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const bool issuer = half == 0 && lane == 0;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
+        const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
+        uint32_t g = 0;                                      // running chunk counter (slot = g % kBtSlots)
+        int pending = -1;                                    // issuer: slot whose TMA store may still be reading smem
+        bool alive = true;
+        long long w_t2f = 0, w_cf = 0, w_t1f = 0, w_bulk = 0, w_nb = 0;
+
+        // One 64-column chunk: TMEM -> (+bias, +residual already in the slot) -> ReLU -> bf16 in place -> TMA store.
+        auto do_chunk = [&](uint32_t tcol, const float* bias, bool has_res, uint32_t release_bar, const CUtensorMap* tm_out, int col,
+                            int row) {
+            const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
+            uint32_t r[32];
+            tmem_ld32(lane_base + tcol, r);
+            float4 bq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + j);
+            if (!timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf)) alive = false;
+            uint8_t* srow = slots + slot * kBtChunkBytes + slab_off;
+            uint4 rq[4];
+            if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
+            }
+            tmem_ld_wait();
+            if (release_bar != 0) {                          // accumulator fully read: hand TMEM back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(release_bar);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
+                float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
+                float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
+                float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                if (has_res) {
+                    v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
+                    v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+                }
+                uint4 o;
+                o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
+                o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
+                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4)) = o;
+            }
+            fence_async_smem();
+            long long tb = clock64();
+            named_bar_sync(1 + quarter, 64);                 // both column halves of this quarter's slab are written
+            w_nb += clock64() - tb;
+            if (issuer) {
+                tma_store_2d(tm_out, slots_base + slot * kBtChunkBytes + quarter * (32 * 128), col, row + quarter * 32);
+                bulk_commit();
+                if (pending >= 0) {                          // the previous store has left shared memory: recycle its slot
+                    tb = clock64();
+                    bulk_wait_read<1>();
+                    w_bulk += clock64() - tb;
+                    mbar_arrive(cempty0 + 8 * pending);
+                }
+                pending = static_cast<int>(slot);
+            }
+            ++g;
+        };
+
+        uint32_t q = 0;
+        for (int i = 0; i < n_i + kBtLag && alive; ++i) {
+            if (i >= kBtLag) {
+                const int m3 = tile_of(i - kBtLag);
+                for (int c = 0; c < Cfg::kNCH && alive; ++c, ++q) {
+                    const uint32_t s = q & 1u;
+                    if (!timed_wait(t2full0 + 8 * s, (q >> 1) & 1u, p.err_flag, 31, w_t2f)) { alive = false; break; }
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc)
+                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, p.bias3 + c * kBtN3 + cc * kBtChunkCols, true,
+                                 cc == kBtN3 / kBtChunkCols - 1 ? t2empty0 + 8 * s : 0u, &tmOut, c * kBtN3 + cc * kBtChunkCols,
+                                 m3 * kTcBlockM);
+                }
+            }
+            if (i < n_i && alive) {
+                const int m2 = tile_of(i);
+                const uint32_t a = static_cast<uint32_t>(i) % Cfg::kNA, ause = static_cast<uint32_t>(i) / Cfg::kNA;
+                if (!timed_wait(t1full0 + 8 * a, ause & 1u, p.err_flag, 32, w_t1f)) { alive = false; break; }
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < P / kBtChunkCols && alive; ++cc)
+                    do_chunk(a * P + cc * kBtChunkCols, p.bias2 + cc * kBtChunkCols, false, cc == P / kBtChunkCols - 1 ? t1empty0 + 8 * a : 0u,
+                             &tmY2s, cc * kBtChunkCols, m2 * kTcBlockM);
+                if (issuer) {                                // Y2[m2] must be complete in global memory before it is reloaded
+                    const long long tb = clock64();
+                    bulk_wait_all();
+                    w_bulk += clock64() - tb;
+                    if (pending >= 0) mbar_arrive(cempty0 + 8 * pending);
+                    pending = -1;
+                    fence_proxy_async_all();
+                    mbar_arrive(y2ready0 + 8 * (i & 1));
+                }
+            }
+        }
+        if (issuer) bulk_wait_read<0>();                     // staged data must stay valid until every store has read it
+        if (p.prof && warp == 4 && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[7] = w_t2f; o[8] = w_cf; o[9] = w_t1f; o[10] = w_bulk; o[11] = w_nb;
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <int P>
+int bt_launch_p(const BtLaunch& l, int num_sms, cudaStream_t stream) {
+    const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
+    HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
+                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.p));
+    return 0;
+}
+
+}  // namespace
+
+int bt_init() {
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
+    return 0;
+}
+
+int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream) {
+    if (l.p.num_m_tiles <= 0) return 0;
+    switch (l.planes) {
+        case 64: return bt_launch_p<64>(l, num_sms, stream);
+        case 128: return bt_launch_p<128>(l, num_sms, stream);
+        case 256: return bt_launch_p<256>(l, num_sms, stream);
+    }
+    set_error("bt_launch: unsupported bottleneck width " + std::to_string(l.planes));
+    return 1;
+}
+
+}  // namespace hmv

@@ -65,4 +65,22 @@ int tc_make_tmap_out(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
 int tc_pick_bn(int n);                                       // tile width for a given output width
 int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream);
 
+// ---- fused bottleneck tail (bottleneck_tc.cu): conv3x3+BN+ReLU -> conv1x1+BN+residual+ReLU in one kernel ----------
+struct BtParams {
+    int num_m_tiles;
+    int tpi, hbox, cblks;              // conv2 tile geometry (as TcParams) ; cblks = P / 64
+    TcTap taps[kTcMaxTaps];
+    const float* bias2;                // [P]   folded BN of conv2
+    const float* bias3;                // [4P]  folded BN of conv3
+    int* err_flag;
+    long long* prof;                   // optional [grid][16] stall counters (HMV_BT_PROF=1), else null
+};
+struct BtLaunch {
+    CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes;
+    BtParams p;
+    int planes;                        // P in {64, 128, 256}
+};
+int bt_init();                                               // shared-memory attributes of the three instantiations
+int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream);
+
 }  // namespace hmv

@@ -89,14 +89,21 @@ struct HostTensor {
     std::vector<int64_t> dims;
 };
 
-enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3 };
+enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4 };
 struct Step {
     int kind;
     std::string name;
-    int layer = -1;                               // index into layers for SK_GEMM
+    int layer = -1;                               // index into layers (SK_GEMM) or tails (SK_TAIL)
     const void* in = nullptr;
     void* out = nullptr;
     int C = 0, H = 0, W = 0;                      // output geometry (NHWC)
+};
+
+// conv2 + conv3 (+residual) of one bottleneck as a single launch (bottleneck_tc.cu)
+struct FusedTail {
+    std::string name;
+    int l2 = -1, l3 = -1;                         // the two layers it covers (weights, biases, maps live there)
+    BtLaunch bt{};
 };
 
 struct FusionLayerPlan {
@@ -123,6 +130,8 @@ struct hmv_handle {
     std::vector<void*> allocs;
     std::vector<Layer> layers;
     std::vector<Step> backbone;
+    std::vector<FusedTail> tails;
+    int fuse_mask = 3;                            // bottleneck widths whose conv2+conv3 run fused: bit0 P=64, bit1 P=128, bit2 P=256 (HMV_FUSE_TAIL=<mask>)
     std::vector<FusionLayerPlan> fusion;
     int pose0 = -1, pose3 = -1, samp = -1;
     // buffers
@@ -157,7 +166,7 @@ struct hmv_handle {
     float *g_x = nullptr, *g_bbox = nullptr, *g_intr = nullptr, *g_hm = nullptr, *g_xy = nullptr, *g_j = nullptr;
     // optional per-launch profiling of the tensor-core GEMM kernel (bench.py roofline leg)
     bool profiling = false;
-    struct ProfRec { int layer; int units; cudaEvent_t e0, e1; };
+    struct ProfRec { int layer; int units; cudaEvent_t e0, e1; int tail; };   // tail >= 0: fused conv2+conv3 launch
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase id, event) recorded while profiling
@@ -367,7 +376,7 @@ static int run_layer(hmv_handle* h, Layer& L, int units, cudaStream_t s, void* o
         HMV_CUDA(cudaEventRecord(ev[0], s));
         const int rc = tc_launch(t, h->num_sms, s);
         HMV_CUDA(cudaEventRecord(ev[1], s));
-        h->prof.push_back({static_cast<int>(&L - h->layers.data()), units, ev[0], ev[1]});
+        h->prof.push_back({static_cast<int>(&L - h->layers.data()), units, ev[0], ev[1], -1});
         return rc;
     }
     ConvF32Params p{};
@@ -384,6 +393,49 @@ static int run_layer(hmv_handle* h, Layer& L, int units, cudaStream_t s, void* o
     p.ep.M = M;
     if (out_override) p.ep.out = out_override;
     return conv_f32_launch(p, s);
+}
+
+// Enqueue a fused conv2+conv3 bottleneck tail for `units` images.
+static int run_tail(hmv_handle* h, int tail, int units, cudaStream_t s) {
+    FusedTail& T = h->tails[tail];
+    if (units == 0) return 0;
+    HMV_CHECK(units <= h->layers[T.l2].max_units, "run_tail: batch exceeds the workspace of " + T.name);
+    ++h->launches;
+    BtLaunch b = T.bt;
+    b.p.num_m_tiles = units * b.p.tpi;
+    static const bool bt_prof = [] { const char* e = getenv("HMV_BT_PROF"); return e && e[0] == '1'; }();
+    if (bt_prof) {                                    // bring-up aid: per-role stall cycles of one launch, printed to stderr
+        static long long* dbuf = nullptr;
+        static int printed = 0;
+        if (!dbuf) HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 148 * 16 * sizeof(long long)));
+        HMV_CUDA(cudaMemsetAsync(dbuf, 0, 148 * 16 * sizeof(long long), s));
+        b.p.prof = dbuf;
+        const int rc = bt_launch(b, h->num_sms, s);
+        if (rc == 0 && units >= 64 && printed < 40) {
+            std::vector<long long> host(148 * 16);
+            HMV_CUDA(cudaStreamSynchronize(s));
+            HMV_CUDA(cudaMemcpy(host.data(), dbuf, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double a[16] = {0};
+            const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += static_cast<double>(host[c * 16 + k]) / grid;
+            fprintf(stderr, "[bt_prof] %s tiles/cta %.1f total %.0f | mma: t1empty %.0f full2 %.0f t2empty %.0f full3 %.0f | prod: empty %.0f y2ready %.0f | "
+                    "epi: t2full %.0f cfull %.0f t1full %.0f bulk %.0f namedbar %.0f | res: cempty %.0f (cycles, mean over CTAs)\n",
+                    T.name.c_str(), a[13], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+            ++printed;
+        }
+        return rc;
+    }
+    if (!h->profiling) return bt_launch(b, h->num_sms, s);
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+        if (!h->ev_pool.empty()) { ev[i] = h->ev_pool.back(); h->ev_pool.pop_back(); }
+        else HMV_CUDA(cudaEventCreate(&ev[i]));
+    }
+    HMV_CUDA(cudaEventRecord(ev[0], s));
+    const int rc = bt_launch(b, h->num_sms, s);
+    HMV_CUDA(cudaEventRecord(ev[1], s));
+    h->prof.push_back({T.l2, units, ev[0], ev[1], tail});
+    return rc;
 }
 
 static Epilogue make_ep(void* out, int ldc, int out_mode, int act) {
@@ -480,6 +532,36 @@ static int add_gemm_step(hmv_handle* h, const std::string& name, int layer, void
     return 0;
 }
 
+// Fused launch plan for the conv2 (3x3) / conv3 (1x1 + residual) pair of one bottleneck; reuses the tensor maps the
+// two layers already own and adds the reload map of the conv2 output and the chunked conv3 weight map.
+static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
+    const Layer& A = h->layers[l2];
+    const Layer& B = h->layers[l3];
+    const int P = A.cout;
+    HMV_CHECK((P == 64 || P == 128 || P == 256) && A.bn == P && A.cin == P && B.cin == P && B.cout == 4 * P && B.n_alloc == 4 * P,
+              "fused bottleneck tail: unexpected widths in " + name);
+    HMV_CHECK(A.tc.mode != TC_DIRECT && B.tc.mode == TC_STORE_RES && A.kind != LK_FLAT, "fused bottleneck tail: unexpected layer plan in " + name);
+    FusedTail T;
+    T.name = name; T.l2 = l2; T.l3 = l3;
+    BtLaunch& b = T.bt;
+    memset(&b.p, 0, sizeof(b.p));
+    b.planes = P;
+    b.tmA = A.tc.tmA; b.tmW2 = A.tc.tmB; b.tmY2s = A.tc.tmC;
+    b.tmOut = B.tc.tmC; b.tmRes = B.tc.tmR;
+    const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
+    if (tc_make_tmap_out(&b.tmY2l, A.ep.out, P, rows, 128) || tc_make_tmap_out(&b.tmW3, B.w, P, 4 * P, 128)) {
+        set_error(std::string(get_error()) + " [fused-tail maps of " + name + "]");
+        return 1;
+    }
+    b.p.tpi = A.tc.p.tpi; b.p.hbox = A.tc.p.hbox; b.p.cblks = A.tc.p.cblks;
+    HMV_CHECK(A.tc.p.num_taps == 9 && b.p.cblks * 64 == P, "fused bottleneck tail: conv2 must be a 3x3 with P input channels");
+    for (int t = 0; t < 9; ++t) b.p.taps[t] = A.tc.p.taps[t];
+    b.p.bias2 = A.bias; b.p.bias3 = B.bias;
+    b.p.err_flag = h->err_flag_dev;
+    h->tails.push_back(T);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan: buffers, layers, descriptors (hmv_prepare)
 // ------------------------------------------------------------------------------------------------
@@ -552,8 +634,10 @@ static int build_backbone(hmv_handle* h) {
             int idx;
             if (add_conv(h, sp + ".conv1", p + ".conv1", p + ".bn1", false, C, pl, 1, 1, H, W, cur, h->bufT1, ACT_RELU, nullptr, &idx)) return 1;
             add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W);
-            if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx)) return 1;
-            add_gemm_step(h, sp + ".conv2", idx, h->bufT2, pl, H / st, W / st);
+            int idx2;
+            if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx2)) return 1;
+            const bool fuse = h->bf16 && ((h->fuse_mask >> li) & 1);
+            if (!fuse) add_gemm_step(h, sp + ".conv2", idx2, h->bufT2, pl, H / st, W / st);
             const void* res = cur;
             if (ds) {
                 if (add_conv(h, sp + ".downsample", p + ".downsample.0", p + ".downsample.1", false, C, pl * 4, 1, st, H, W, cur, h->bufDS, ACT_NONE, nullptr, &idx)) return 1;
@@ -561,7 +645,14 @@ static int build_backbone(hmv_handle* h) {
                 res = h->bufDS;
             }
             if (add_conv(h, sp + ".conv3", p + ".conv3", p + ".bn3", false, pl, pl * 4, 1, 1, H / st, W / st, h->bufT2, nxt, ACT_RELU, res, &idx)) return 1;
-            add_gemm_step(h, sp + ".conv3", idx, nxt, pl * 4, H / st, W / st);
+            if (fuse) {
+                if (add_tail(h, sp + ".conv3", idx2, idx)) return 1;
+                Step ts; ts.kind = SK_TAIL; ts.name = sp + ".conv3"; ts.layer = static_cast<int>(h->tails.size()) - 1;
+                ts.out = nxt; ts.C = pl * 4; ts.H = H / st; ts.W = W / st;
+                h->backbone.push_back(ts);
+            } else {
+                add_gemm_step(h, sp + ".conv3", idx, nxt, pl * 4, H / st, W / st);
+            }
             void* t = cur; cur = nxt; nxt = t;
             C = pl * 4; H /= st; W /= st;
         }
@@ -746,6 +837,8 @@ static int run_backbone_t(hmv_handle* h, const float* x, int n_img, int num_step
             ++h->launches;
             if (stem_pool_launch(x, static_cast<const bf16*>(h->stem_w), h->stem_b, static_cast<bf16*>(st.out), n_img, h->num_sms,
                                  h->err_flag_dev, s)) return 1;
+        } else if (st.kind == SK_TAIL) {
+            if (run_tail(h, st.layer, n_img, s)) return 1;
         } else if (st.kind == SK_MAXPOOL) {
             ++h->launches;
             if (maxpool_launch<T>(static_cast<const T*>(st.in), static_cast<T*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s)) return 1;
@@ -901,7 +994,11 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
         return 1;
     }
     *h->err_flag_host = 0;
-    if (h->bf16 && hmv::tc_init()) { delete h; return 1; }
+    if (h->bf16 && (hmv::tc_init() || hmv::bt_init())) { delete h; return 1; }
+    {
+        const char* e = getenv("HMV_FUSE_TAIL");
+        if (e && e[0] >= '0' && e[0] <= '7') h->fuse_mask = e[0] - '0';
+    }
     *out = h;
     return 0;
 }
@@ -1366,9 +1463,18 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         const hmv::Layer& L = h->layers[r.layer];
         const double M = static_cast<double>(r.units) * L.rows_per_unit();
         const double kreal = L.kind == hmv::LK_STEM ? 147.0 : (L.kind == hmv::LK_FLAT ? static_cast<double>(L.cin) : static_cast<double>(L.cin) * L.ksize * L.ksize);
-        const double flop = 2.0 * M * L.cout * kreal;
+        double flop = 2.0 * M * L.cout * kreal;
+        std::string name = L.name;
+        int ncol = L.cout;
+        double kcol = kreal;
+        if (r.tail >= 0) {                            // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3
+            const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
+            flop += 2.0 * M * L3.cout * L3.cin;
+            name = L.name + "+conv3";
+            ncol = L3.cout; kcol = kreal + L3.cin;
+        }
         ms += t; fl += flop;
-        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f\n", L.name.c_str(), M, L.cout, kreal, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12);
+        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12);
         h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
     }
     if (f) fclose(f);
