@@ -156,6 +156,12 @@ struct hmv_handle {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     float *d_bbox = nullptr, *d_intr = nullptr, *d_hm = nullptr, *d_xy = nullptr, *d_j = nullptr;
     int host_cap = 0;
+    // asynchronous host calls (hmv_forward_host_async / hmv_host_wait): the staging ring runs across calls, so the
+    // copies of call k+1 overlap the compute of call k; one completion event per in-flight call
+    int64_t chunk_seq = 0;                        // staging chunks issued so far (buffer = chunk_seq & 1)
+    static constexpr int kMaxInflight = 4;
+    cudaEvent_t ev_done[kMaxInflight] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t tickets_issued = 0, tickets_waited = 0;
     // CUDA graphs for small batches (launch-bound regime, B=1 latency): one instantiated graph per batch size over
     // internal I/O buffers; calls 1 and 2 with a batch size run eagerly / capture, later calls replay.
     struct GraphSlot { int calls = 0; int kernels = 0; cudaGraphExec_t exec = nullptr; };
@@ -1018,6 +1024,7 @@ int hmv_destroy(hmv_handle* h) {
     if (h->d_hm) cudaFree(h->d_hm);
     if (h->d_xy) cudaFree(h->d_xy);
     if (h->d_j) cudaFree(h->d_j);
+    for (auto e : h->ev_done) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
     for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1184,16 +1191,12 @@ static int ensure_host_pipeline(hmv_handle* h, int batch) {
     return 0;
 }
 
-int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
-                     float* joints_crop_img, float* joints_cam) {
-    HMV_CHECK(h && h->prepared, "hmv_forward_host: handle not prepared");
-    HMV_CHECK(batch >= 0, "negative batch");
-    if (batch == 0) return 0;
-    HMV_CHECK(x, "hmv_forward_host: x is null");
-    HMV_CHECK(!h->cfg.use_crop || (bbox && intr), "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
-    HMV_CUDA(cudaSetDevice(h->cfg.device));
-    if (hmv::check_flag(h)) return 1;
-    if (ensure_host_pipeline(h, batch)) return 1;
+// Enqueue one host-buffer forward: x is staged through two device buffers (copy stream) while the compute stream
+// works on the previous chunk; bbox / intrinsics / outputs travel on the compute stream.  `ramp` uses two smaller
+// first chunks so that compute starts after a short copy (synchronous calls); asynchronous calls keep full chunks
+// because the copy of their first chunk already overlaps the previous call.
+static int enqueue_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
+                        float* joints_crop_img, float* joints_cam, bool ramp) {
     const size_t per_sample_x = static_cast<size_t>(h->V) * 3 * h->img * h->img;
     const size_t nimg = static_cast<size_t>(batch) * h->V;
     cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
@@ -1205,14 +1208,12 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
     for (int p0 = 0; p0 < batch; p0 += h->fcap) {
         const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
         for (int s0 = p0; s0 < p0 + np; ++chunk) {
-            // The first two chunks of a call are smaller (mb/4, 3*mb/4) so that compute starts after a short copy;
-            // afterwards copies of full micro-batches are hidden behind the previous chunk's compute.
             int cap = h->mb;
-            if (h->mb >= 8 && chunk == 0) cap = h->mb / 4;
-            else if (h->mb >= 8 && chunk == 1) cap = h->mb - h->mb / 4;
+            if (ramp && h->mb >= 8 && chunk == 0) cap = h->mb / 4;
+            else if (ramp && h->mb >= 8 && chunk == 1) cap = h->mb - h->mb / 4;
             const int n = p0 + np - s0 < cap ? p0 + np - s0 : cap;
-            const int b = chunk & 1;
-            if (chunk >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
+            const int b = static_cast<int>(h->chunk_seq & 1);
+            if (h->chunk_seq >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
             HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x + s0 * per_sample_x, per_sample_x * n * sizeof(float), cudaMemcpyHostToDevice, cs));
             HMV_CUDA(cudaEventRecord(h->ev_copied[b], cs));
             HMV_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[b], 0));
@@ -1222,6 +1223,7 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
                                h->d_xy + static_cast<size_t>(s0) * h->V * 21 * 2, ks))
                 return 1;
             HMV_CUDA(cudaEventRecord(h->ev_consumed[b], ks));
+            ++h->chunk_seq;
             s0 += n;
         }
         if (hmv::run_back(h, np, h->d_j + static_cast<size_t>(p0) * 21 * 3, ks)) return 1;
@@ -1229,8 +1231,55 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
     if (heatmap) HMV_CUDA(cudaMemcpyAsync(heatmap, h->d_hm, nimg * 21 * h->hm * h->hm * sizeof(float), cudaMemcpyDeviceToHost, ks));
     if (joints_crop_img) HMV_CUDA(cudaMemcpyAsync(joints_crop_img, h->d_xy, nimg * 21 * 2 * sizeof(float), cudaMemcpyDeviceToHost, ks));
     if (joints_cam) HMV_CUDA(cudaMemcpyAsync(joints_cam, h->d_j, static_cast<size_t>(batch) * 21 * 3 * sizeof(float), cudaMemcpyDeviceToHost, ks));
-    HMV_CUDA(cudaStreamSynchronize(ks));
-    HMV_CUDA(cudaStreamSynchronize(cs));
+    return 0;
+}
+
+static int host_call_checks(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, const char* who) {
+    HMV_CHECK(h && h->prepared, std::string(who) + ": handle not prepared");
+    HMV_CHECK(batch >= 0, "negative batch");
+    HMV_CHECK(x || batch == 0, std::string(who) + ": x is null");
+    HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
+    HMV_CUDA(cudaSetDevice(h->cfg.device));
+    return hmv::check_flag(h);
+}
+
+int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
+                     float* joints_crop_img, float* joints_cam) {
+    if (host_call_checks(h, x, bbox, intr, batch, "hmv_forward_host")) return 1;
+    if (batch == 0) return 0;
+    HMV_CHECK(h->tickets_issued == h->tickets_waited, "hmv_forward_host: asynchronous calls are still in flight (hmv_host_wait them first)");
+    if (ensure_host_pipeline(h, batch)) return 1;
+    if (enqueue_host(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, /*ramp=*/true)) return 1;
+    HMV_CUDA(cudaStreamSynchronize(h->compute_stream));
+    HMV_CUDA(cudaStreamSynchronize(h->copy_stream));
+    return hmv::check_flag(h);
+}
+
+int hmv_forward_host_async(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
+                           float* joints_crop_img, float* joints_cam, int64_t* ticket) {
+    if (host_call_checks(h, x, bbox, intr, batch, "hmv_forward_host_async")) return 1;
+    HMV_CHECK(ticket, "hmv_forward_host_async: ticket is null");
+    HMV_CHECK(batch > 0, "hmv_forward_host_async: empty batch");
+    HMV_CHECK(h->tickets_issued - h->tickets_waited < hmv_handle::kMaxInflight, "hmv_forward_host_async: too many calls in flight");
+    if (batch > h->host_cap && h->tickets_issued != h->tickets_waited) {      // growing the output buffers frees the old ones
+        hmv::set_error("hmv_forward_host_async: batch larger than any earlier call while calls are in flight");
+        return 1;
+    }
+    if (ensure_host_pipeline(h, batch)) return 1;
+    if (enqueue_host(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, /*ramp=*/h->tickets_issued == h->tickets_waited)) return 1;
+    const int slot = static_cast<int>(h->tickets_issued % hmv_handle::kMaxInflight);
+    if (!h->ev_done[slot]) HMV_CUDA(cudaEventCreateWithFlags(&h->ev_done[slot], cudaEventDisableTiming));
+    HMV_CUDA(cudaEventRecord(h->ev_done[slot], h->compute_stream));
+    *ticket = h->tickets_issued++;
+    return 0;
+}
+
+int hmv_host_wait(hmv_handle* h, int64_t ticket) {
+    HMV_CHECK(h && h->prepared, "hmv_host_wait: handle not prepared");
+    HMV_CHECK(ticket >= h->tickets_waited && ticket < h->tickets_issued, "hmv_host_wait: unknown or already waited ticket (tickets complete in order)");
+    HMV_CUDA(cudaSetDevice(h->cfg.device));
+    HMV_CUDA(cudaEventSynchronize(h->ev_done[ticket % hmv_handle::kMaxInflight]));   // the stream is in-order: earlier tickets are done too
+    h->tickets_waited = ticket + 1;
     return hmv::check_flag(h);
 }
 

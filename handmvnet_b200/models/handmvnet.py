@@ -148,6 +148,30 @@ class _JointsDecoderGCN(_NoEagerPath):
         self.joints_gcn3 = _ChebConv(64, out_dim)
 
 
+class HostTicket:
+    """One in-flight forward_host_async call.  result() blocks until it has completed and returns the output dict;
+    with recycle=True the pinned output buffers go back to the model's pool (they are overwritten by a later call), so
+    clone what must outlive the next calls."""
+
+    def __init__(self, model, ticket, inputs, outputs, pool):
+        self._model, self._ticket, self._inputs, self._outputs, self._pool = model, ticket, inputs, outputs, pool
+        self._done = False
+
+    def result(self, recycle=False):
+        if not self._done:
+            _lib.check(_lib.load().hmv_host_wait(self._model._handle, self._ticket), "hmv_host_wait")
+            self._done = True
+            self._inputs = None
+        hm, j2d, j3d = self._outputs
+        out = {"joints_crop_img": j2d, "joints_cam": j3d}
+        if hm is not None:
+            out["heatmap"] = hm
+        if recycle and self._pool is not None:
+            self._pool.append(self._outputs)
+            self._pool = None
+        return out
+
+
 class HandMvNet(nn.Module):
     """`HandMvNet(train_params, model_params, data_params)` - reference handmvnet.py:28.
 
@@ -366,6 +390,36 @@ class HandMvNet(nn.Module):
         if want_heatmap:
             out["heatmap"] = hm
         return out
+
+    @torch.no_grad()
+    def forward_host_async(self, x, bbox=None, cam_params=None, device=None, want_heatmap=True):
+        """Streaming form of forward_host: enqueues one batch and returns a HostTicket at once; the copies of the next
+        call overlap this call's compute (hmv_forward_host_async).  `ticket.result()` waits and returns the CPU
+        tensors.  The input tensors must be pinned or at least stay alive and unmodified until then."""
+        if x.device.type != "cpu":
+            raise ValueError("forward_host_async expects CPU tensors")
+        b, v, intr = self._check_inputs(x, bbox, cam_params)
+        if self._handle is None:
+            self.prepare(device if device is not None else next(self.parameters()).device)
+        crop = "crop" in self.pos_enc_list
+        x = x.to(torch.float32).contiguous()
+        bbox_f = bbox.to(torch.float32).contiguous() if crop else None
+        intr_f = intr.to(torch.float32).contiguous() if crop else None
+        pool = self.__dict__.setdefault("_host_out_pool", {})
+        key = (b, v, bool(want_heatmap))
+        free = pool.setdefault(key, [])
+        if free:
+            hm, j2d, j3d = free.pop()
+        else:
+            pin = torch.cuda.is_available()
+            hm = torch.empty((b, v, NUM_JOINTS, 32, 32), dtype=torch.float32, pin_memory=pin) if want_heatmap else None
+            j2d = torch.empty((b, v, NUM_JOINTS, 2), dtype=torch.float32, pin_memory=pin)
+            j3d = torch.empty((b, NUM_JOINTS, 3), dtype=torch.float32, pin_memory=pin)
+        t = ctypes.c_int64(-1)
+        _lib.check(_lib.load().hmv_forward_host_async(self._handle, _lib.ptr(x), _lib.ptr(bbox_f), _lib.ptr(intr_f), b,
+                                                      _lib.ptr(hm), _lib.ptr(j2d), _lib.ptr(j3d), ctypes.byref(t)),
+                   "hmv_forward_host_async")
+        return HostTicket(self, t.value, (x, bbox_f, intr_f), (hm, j2d, j3d), free)
 
     def synchronize(self):
         if self._handle is not None:

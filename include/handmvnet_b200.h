@@ -66,6 +66,15 @@ int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* i
 int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch,
                      float* heatmap, float* joints_crop_img, float* joints_cam);
 
+/* Streaming form of hmv_forward_host for a caller that feeds batch after batch (the loop of
+ * src/eval_fps.py:79-92 / the Lightning test loop): enqueues the copies and kernels of one batch and returns
+ * a ticket without waiting, so the host->device copies of call k+1 overlap the compute of call k.  At most 4
+ * calls may be in flight; host buffers (inputs AND outputs) must stay valid until hmv_host_wait(ticket) has
+ * returned.  Tickets complete in issue order. */
+int hmv_forward_host_async(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch,
+                           float* heatmap, float* joints_crop_img, float* joints_cam, int64_t* ticket);
+int hmv_host_wait(hmv_handle* h, int64_t ticket);
+
 /* Blocks until the handle's work is done and reports device-side pipeline errors. */
 int hmv_synchronize(hmv_handle* h);
 

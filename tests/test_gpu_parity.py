@@ -227,6 +227,18 @@ def test_micro_batching_and_host_path_are_consistent(precision):
     hcpu = m_small.forward_host(x.pin_memory(), bbox.pin_memory(), {"intrinsic": intr.pin_memory()})
     for k in a:
         assert torch.equal(hcpu[k], a[k]), k
+    # streaming host entry point: three batches in flight back to back, each must equal its blocking result
+    xs = [x.pin_memory(), x.flip(0).contiguous().pin_memory(), (x * 0.5).pin_memory()]
+    bb, it = bbox.pin_memory(), intr.pin_memory()
+    want = [_forward(m_small, xi, bbox, intr) for xi in xs]
+    tickets = [m_small.forward_host_async(xi, bb, {"intrinsic": it}) for xi in xs]
+    for tk, w in zip(tickets, want):
+        got = tk.result()
+        for k in w:
+            assert torch.equal(got[k], w[k]), f"async {k}"
+    with pytest.raises(RuntimeError):
+        tickets[0]._done = False
+        tickets[0].result()                      # a ticket can only be waited once, in order
     # empty batch
     e = m_big(x[:0].cuda(), bbox[:0].cuda(), {"intrinsic": intr[:0].cuda()})
     assert e["joints_cam"].shape == (0, 21, 3)
