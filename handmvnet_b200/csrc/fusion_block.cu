@@ -1,0 +1,455 @@
+// One fusion-transformer layer after its QKV projection as ONE kernel (bf16 tensor-core path):
+//   softmax(Q K^T * scale) V  ->  to_out (+bias) + residual  ->  LayerNorm(norm1)  ->  LayerNorm(ff.net.0)
+//   ->  Linear(d,128) + GELU  ->  Linear(128,d) (+bias) + residual  ->  LayerNorm(norm2)
+// (reference MultiHeadAttention.forward, src/models/layers.py:217-236, FeedForward :165-170).
+//
+// A CTA owns 32 query rows of one sample (everything after QKV is row-local except attention, which is per sample):
+//   phase 1  attention, mma.sync m16n8k16 bf16 / fp32 accumulate, flash-style online softmax over 64-key blocks;
+//            8 warps = 4 heads in flight x 2 query m-tiles, two rounds for the 8 heads; the normalised head outputs
+//            overwrite the Q tile in shared memory, which becomes the A operand [32 x 1024] of the out-projection
+//   phase 2  out-projection: warp w owns output columns [72w, 72w+72) (d = 524 padded to 576) for all 32 rows and
+//            streams ITS rows of W_out from L2 through a private 3-stage cp.async ring (no block-wide barriers)
+//   phase 3  + bias + residual (fp32 master copy of the tokens), LayerNorm x2 with block-wide row statistics
+//   phase 4/5 the feed-forward GEMMs with the same streaming helper, hidden activations in shared memory
+//   phase 6  + residual, LayerNorm, fp32 master + bf16 copy of the layer output (pad columns written as zero)
+// so the token stream makes one HBM round trip per layer and the layer is 2 launches (QKV GEMM + this) instead of 7.
+#include "kernels.cuh"
+
+namespace hmv {
+
+namespace {
+
+constexpr int kFbRows = 32;                      // query rows per CTA
+constexpr int kFbHeads = 8, kFbD = 128, kFbInner = kFbHeads * kFbD;
+constexpr int kFbKeys = 64;                      // key block
+constexpr int kFbDp = 576;                       // d_model padded: 8 warps x 72 columns
+constexpr int kFbNt = 9;                         // n8 tiles per warp in the d_model-wide GEMMs
+constexpr int kFbHid = 128;                      // feed-forward hidden width
+constexpr int kFbQPitch = kFbInner + 8;          // bf16 elements; (pitch * 2) % 128 == 16 -> conflict-free ldmatrix
+constexpr int kFbKvPitch = kFbD + 8;
+constexpr int kFbHPitch = kFbDp + 8;
+constexpr int kFbFPitch = kFbHid + 8;
+constexpr int kFbStageBytes = 72 * (32 + 8) * 2; // largest per-warp weight stage: 72 rows x 32 k
+constexpr int kFbQoBytes = kFbRows * kFbQPitch * 2;                       // 66048
+constexpr int kFbKvBytes = 4 * 2 * kFbKeys * kFbKvPitch * 2;              // 139264 (aliased by the weight rings)
+constexpr int kFbRedBytes = 6 * 8 * kFbRows * 4;                          // 6 reductions x [8 warps][32 rows]
+constexpr int kFbSmem = kFbQoBytes + kFbKvBytes + kFbRedBytes;
+static_assert(8 * 3 * kFbStageBytes <= kFbKvBytes, "weight rings alias the K/V blocks");
+static_assert(kFbRows * kFbHPitch * 2 + kFbRows * kFbFPitch * 2 <= kFbQoBytes, "H and F alias the Q/O tile");
+
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bar_pair(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// acc[2][NT][4] += A[32 x K] * W[n0 .. n0 + 8*NT, 0 .. K)^T.   A: shared memory, row-major bf16 (byte pitch a_pitch);
+// W: global, row-major bf16 with leading dimension ldw (already offset to row n0).  The warp streams its W rows in
+// K chunks of KCH through its private 3-stage ring at `ring` (shared address); no block-level synchronisation.
+template <int NT, int KCH>
+__device__ __forceinline__ void warp_stream_gemm(float (&acc)[2][NT][4], uint32_t a_addr, int a_pitch, const bf16* __restrict__ w,
+                                                 int ldw, int K, uint32_t ring, int lane) {
+    constexpr int kPitch = (KCH + 8) * 2;                 // bytes per staged W row
+    constexpr int kStage = NT * 8 * kPitch;
+    constexpr int kPieces = NT * 8 * (KCH / 8);           // 16-byte pieces per chunk
+    static_assert(kStage <= kFbStageBytes && kPieces % 32 == 0, "stage geometry");
+    const int nchunks = K / KCH;
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            const uint32_t dst = ring + (c % 3) * kStage;
+#pragma unroll
+            for (int i = 0; i < kPieces / 32; ++i) {
+                const int idx = lane + 32 * i;
+                const int row = idx / (KCH / 8), pc = idx % (KCH / 8);
+                cp16(dst + row * kPitch + pc * 16, w + static_cast<size_t>(row) * ldw + c * KCH + pc * 8);
+            }
+        }
+        cp_commit();
+    };
+    issue(0);
+    issue(1);
+    const uint32_t a_lane = a_addr + (lane & 15) * a_pitch + (lane >> 4) * 16;
+    const uint32_t b_lane = ((lane & 7) + (lane >> 4) * 8) * kPitch + ((lane >> 3) & 1) * 16;
+    const uint32_t b_lane2 = (lane & 7) * kPitch + ((lane >> 3) & 1) * 16;           // x2 form: lanes 0-15 address
+    for (int c = 0; c < nchunks; ++c) {
+        issue(c + 2);
+        cp_wait<2>();
+        __syncwarp();
+        const uint32_t wst = ring + (c % 3) * kStage;
+#pragma unroll
+        for (int kk = 0; kk < KCH / 16; ++kk) {
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                ldsm4(a_lane + mt * 16 * a_pitch + (c * KCH + kk * 16) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldsm4(wst + b_lane + np * 16 * kPitch + kk * 32, b0, b1, b2, b3);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma16816(acc[mt][2 * np], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                    mma16816(acc[mt][2 * np + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
+                }
+            }
+            if (NT & 1) {
+                uint32_t b0, b1;
+                ldsm2(wst + b_lane2 + (NT - 1) * 8 * kPitch + kk * 32, b0, b1);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][NT - 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+            }
+        }
+        __syncwarp();                                     // the stage is rewritten two iterations from now
+    }
+    cp_wait<0>();
+}
+
+// Block-wide sum over the columns of each of the 32 rows.  part[mt*2 + hi] is this thread's partial for row
+// mt*16 + g + 8*hi; `red` is a [8 warps][32 rows] scratch used by exactly one call.
+__device__ __forceinline__ void row_sums(float (&part)[4], float* red, int warp, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1);
+        part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2);
+    }
+    const int g = lane >> 2;
+    if ((lane & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp * kFbRows + (i >> 1) * 16 + g + (i & 1) * 8] = part[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * kFbRows + (i >> 1) * 16 + g + (i & 1) * 8];
+        part[i] = s;
+    }
+}
+
+// Row statistics (mean, 1/std) of the 32 x d tile held in the accumulator layout; entry mt*2 + hi is row mt*16 + g + 8*hi.
+__device__ __forceinline__ void layer_norm_stats(const float (&v)[2][kFbNt][4], int col0, int d, float* red, int warp, int lane,
+                                                 float (&mean)[4], float (&rstd)[4]) {
+    const int t = lane & 3;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < kFbNt; ++nt) {
+            part[mt * 2] += v[mt][nt][0] + v[mt][nt][1];        // columns >= d hold exact zeros
+            part[mt * 2 + 1] += v[mt][nt][2] + v[mt][nt][3];
+        }
+    row_sums(part, red, warp, lane);
+    const float inv_d = 1.f / static_cast<float>(d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mean[i] = part[i] * inv_d; part[i] = 0.f; }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < kFbNt; ++nt) {
+            const int c = col0 + nt * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float dv = (c + (e & 1)) < d ? v[mt][nt][e] - mean[mt * 2 + (e >> 1)] : 0.f;
+                part[mt * 2 + (e >> 1)] += dv * dv;
+            }
+        }
+    row_sums(part, red + 8 * kFbRows, warp, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rstd[i] = rsqrtf(part[i] * inv_d + 1e-5f);
+}
+
+// LayerNorm of one accumulator element (row statistics from layer_norm_stats); pad columns stay zero.
+__device__ __forceinline__ float ln_apply(float x, float mean, float rstd, float gamma, float beta, bool valid) {
+    return valid ? (x - mean) * rstd * gamma + beta : 0.f;
+}
+
+// In-place LayerNorm of the tile.
+__device__ __forceinline__ void layer_norm_tile(float (&v)[2][kFbNt][4], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                int col0, int d, float* red, int warp, int lane) {
+    float mean[4], rstd[4];
+    layer_norm_stats(v, col0, d, red, warp, lane, mean, rstd);
+    const int t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < kFbNt; ++nt) {
+        const int c = col0 + nt * 8 + 2 * t;
+        const float2 gq = __ldg(reinterpret_cast<const float2*>(gamma + c)), bq = __ldg(reinterpret_cast<const float2*>(beta + c));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                v[mt][nt][e] = ln_apply(v[mt][nt][e], mean[mt * 2 + (e >> 1)], rstd[mt * 2 + (e >> 1)], (e & 1) ? gq.y : gq.x,
+                                        (e & 1) ? bq.y : bq.x, (c + (e & 1)) < d);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) fusion_block_kernel(const FusionBlockParams p) {
+    pdl_wait();
+    extern __shared__ __align__(128) uint8_t fb_smem[];
+    bf16* qo = reinterpret_cast<bf16*>(fb_smem);
+    uint8_t* region = fb_smem + kFbQoBytes;
+    float* red = reinterpret_cast<float*>(fb_smem + kFbQoBytes + kFbKvBytes);
+    const uint32_t qo_addr = static_cast<uint32_t>(__cvta_generic_to_shared(qo));
+    const uint32_t region_addr = static_cast<uint32_t>(__cvta_generic_to_shared(region));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int b = blockIdx.y, q0 = blockIdx.x * kFbRows;
+    const int rows_valid = p.nq - q0 < kFbRows ? p.nq - q0 : kFbRows;
+    const size_t in_row0 = static_cast<size_t>(b) * p.s_in + q0;         // first query row in the qkv / residual streams
+    const size_t out_row0 = static_cast<size_t>(b) * p.nq + q0;
+
+    // ---------------- phase 1: attention ----------------
+    {
+        const bf16* qsrc = p.qkv + in_row0 * p.ld_qkv;
+        for (int i = threadIdx.x; i < kFbRows * (kFbInner / 8); i += 256) {
+            const int r = i / (kFbInner / 8), c = (i % (kFbInner / 8)) * 8;
+            const uint32_t dst = qo_addr + (r * kFbQPitch + c) * 2;
+            if (r < rows_valid) cp16(dst, qsrc + static_cast<size_t>(r) * p.ld_qkv + c);
+            else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        }
+        cp_commit();
+        cp_wait<0>();
+        __syncthreads();
+
+        const int hs = warp >> 1, mt = warp & 1, pl = threadIdx.x & 63;    // head slot, query m-tile, lane within the pair
+        const uint32_t ks_addr = region_addr + hs * (2 * kFbKeys * kFbKvPitch * 2);
+        const uint32_t vs_addr = ks_addr + kFbKeys * kFbKvPitch * 2;
+        const uint32_t bk_off = (((lane & 7) + (lane >> 4) * 8) * kFbKvPitch + ((lane >> 3) & 1) * 8) * 2;
+        const uint32_t bv_off = (((lane & 7) + ((lane >> 3) & 1) * 8) * kFbKvPitch + (lane >> 4) * 8) * 2;
+        const bf16* kv0 = p.qkv + (static_cast<size_t>(b) * p.s_in + p.kv_row0) * p.ld_qkv + kFbInner;
+        for (int rd = 0; rd < 2; ++rd) {
+            const int head = hs + 4 * rd;
+            const uint32_t a_off = qo_addr + ((mt * 16 + (lane & 15)) * kFbQPitch + head * kFbD + (lane >> 4) * 8) * 2;
+            float o[16][4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+            for (int j0 = 0; j0 < p.nk; j0 += kFbKeys) {
+                bar_pair(1 + hs);                                          // both warps are done with the previous block
+                const int kvalid = p.nk - j0 < kFbKeys ? p.nk - j0 : kFbKeys;
+                const bf16* ksrc = kv0 + static_cast<size_t>(j0) * p.ld_qkv + head * kFbD;
+                for (int i = pl; i < kFbKeys * 16; i += 64) {
+                    const int r = i >> 4, c = (i & 15) * 8;
+                    const uint32_t off = (r * kFbKvPitch + c) * 2;
+                    if (r < kvalid) {
+                        cp16(ks_addr + off, ksrc + static_cast<size_t>(r) * p.ld_qkv + c);
+                        cp16(vs_addr + off, ksrc + static_cast<size_t>(r) * p.ld_qkv + kFbInner + c);
+                    } else {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ks_addr + off), "r"(0u) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vs_addr + off), "r"(0u) : "memory");
+                    }
+                }
+                cp_commit();
+                cp_wait<0>();
+                bar_pair(1 + hs);
+                float sc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
+#pragma unroll
+                for (int kk = 0; kk < kFbD / 16; ++kk) {
+                    uint32_t a0, a1, a2, a3;
+                    ldsm4(a_off + kk * 32, a0, a1, a2, a3);
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm4(ks_addr + bk_off + np * 16 * kFbKvPitch * 2 + kk * 32, b0, b1, b2, b3);
+                        mma16816(sc[2 * np], a0, a1, a2, a3, b0, b1);
+                        mma16816(sc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+                    }
+                }
+                float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int c = nt * 8 + 2 * t;
+                    if (c >= kvalid) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+                    if (c + 1 >= kvalid) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+                    bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+                    bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+                }
+                bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+                bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+                const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+                const float al0 = exp2f((m0 - mn0) * p.scale_log2e), al1 = exp2f((m1 - mn1) * p.scale_log2e);
+                m0 = mn0; m1 = mn1;
+                float rs0 = 0.f, rs1 = 0.f;
+                uint32_t pa[8][2];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float p0 = exp2f((sc[nt][0] - mn0) * p.scale_log2e), p1 = exp2f((sc[nt][1] - mn0) * p.scale_log2e);
+                    const float p2 = exp2f((sc[nt][2] - mn1) * p.scale_log2e), p3 = exp2f((sc[nt][3] - mn1) * p.scale_log2e);
+                    rs0 += p0 + p1; rs1 += p2 + p3;
+                    pa[nt][0] = pack_bf16x2(p0, p1);
+                    pa[nt][1] = pack_bf16x2(p2, p3);
+                }
+                rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+                rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+                l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+#pragma unroll
+                for (int kk = 0; kk < kFbKeys / 16; ++kk) {
+                    const uint32_t a0 = pa[2 * kk][0], a1 = pa[2 * kk][1], a2 = pa[2 * kk + 1][0], a3 = pa[2 * kk + 1][1];
+#pragma unroll
+                    for (int dp = 0; dp < 8; ++dp) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm4_trans(vs_addr + bv_off + kk * 16 * kFbKvPitch * 2 + dp * 32, b0, b1, b2, b3);
+                        mma16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
+                        mma16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+                    }
+                }
+            }
+            // normalised head output overwrites this warp's own Q rows / head columns (nobody else reads them)
+            const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+            __syncwarp();
+            bf16* orow = qo + (mt * 16 + g) * kFbQPitch + head * kFbD + 2 * t;
+#pragma unroll
+            for (int dt = 0; dt < 16; ++dt) {
+                *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+                *reinterpret_cast<uint32_t*>(orow + 8 * kFbQPitch + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+            }
+        }
+    }
+    __syncthreads();                                          // O complete; K/V blocks are dead -> weight rings
+
+    // ---------------- phase 2: out-projection ----------------
+    const int col0 = warp * 72;
+    const uint32_t ring = region_addr + warp * 3 * kFbStageBytes;
+    float acc[2][kFbNt][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < kFbNt; ++nt) { acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f; }
+    warp_stream_gemm<kFbNt, 32>(acc, qo_addr, kFbQPitch * 2, p.wo + static_cast<size_t>(col0) * kFbInner, kFbInner, kFbInner, ring, lane);
+
+    // ---------------- phase 3: + bias + residual, norm1, ff.net.0 ----------------
+#pragma unroll
+    for (int nt = 0; nt < kFbNt; ++nt) {
+        const int c = col0 + nt * 8 + 2 * t;
+        const float2 bq = __ldg(reinterpret_cast<const float2*>(p.bo + c));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hi = 0; hi < 2; ++hi) {
+                const int r = mt * 16 + g + hi * 8;
+                float2 rv = make_float2(0.f, 0.f);
+                if (r < rows_valid) rv = *reinterpret_cast<const float2*>(p.res_in + (in_row0 + r) * p.pitch + c);
+                acc[mt][nt][hi * 2] += bq.x + rv.x;
+                acc[mt][nt][hi * 2 + 1] += bq.y + rv.y;
+            }
+    }
+    layer_norm_tile(acc, p.g1, p.b1, col0, p.d, red, warp, lane);                      // h = norm1(out + q)
+    __syncthreads();                                          // every warp has finished reading O: H may overwrite it
+    {
+        float mean[4], rstd[4];
+        layer_norm_stats(acc, col0, p.d, red + 2 * 8 * kFbRows, warp, lane, mean, rstd);    // ff.net.0 (h itself stays in acc)
+        bf16* hs = qo;                                        // H [32 x 576] bf16, pitch kFbHPitch
+#pragma unroll
+        for (int nt = 0; nt < kFbNt; ++nt) {
+            const int c = col0 + nt * 8 + 2 * t;
+            const float2 gq = __ldg(reinterpret_cast<const float2*>(p.gff + c)), bq = __ldg(reinterpret_cast<const float2*>(p.bff + c));
+            const bool v0 = c < p.d, v1 = c + 1 < p.d;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                *reinterpret_cast<uint32_t*>(hs + (mt * 16 + g) * kFbHPitch + c) =
+                    pack_bf16x2(ln_apply(acc[mt][nt][0], mean[mt * 2], rstd[mt * 2], gq.x, bq.x, v0),
+                                ln_apply(acc[mt][nt][1], mean[mt * 2], rstd[mt * 2], gq.y, bq.y, v1));
+                *reinterpret_cast<uint32_t*>(hs + (mt * 16 + g + 8) * kFbHPitch + c) =
+                    pack_bf16x2(ln_apply(acc[mt][nt][2], mean[mt * 2 + 1], rstd[mt * 2 + 1], gq.x, bq.x, v0),
+                                ln_apply(acc[mt][nt][3], mean[mt * 2 + 1], rstd[mt * 2 + 1], gq.y, bq.y, v1));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 4: ff.net.1 + GELU (warp w owns hidden columns [16w, 16w+16)) ----------------
+    bf16* fs = qo + kFbRows * kFbHPitch;                      // F [32 x 128] bf16, pitch kFbFPitch
+    {
+        float f1[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { f1[mt][nt][0] = f1[mt][nt][1] = f1[mt][nt][2] = f1[mt][nt][3] = 0.f; }
+        warp_stream_gemm<2, 96>(f1, qo_addr, kFbHPitch * 2, p.w1 + static_cast<size_t>(warp) * 16 * kFbDp, kFbDp, kFbDp, ring, lane);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int c = warp * 16 + nt * 8 + 2 * t;
+            const float2 bq = __ldg(reinterpret_cast<const float2*>(p.bf1 + c));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                *reinterpret_cast<uint32_t*>(fs + (mt * 16 + g) * kFbFPitch + c) =
+                    pack_bf16x2(gelu_erf(f1[mt][nt][0] + bq.x), gelu_erf(f1[mt][nt][1] + bq.y));
+                *reinterpret_cast<uint32_t*>(fs + (mt * 16 + g + 8) * kFbFPitch + c) =
+                    pack_bf16x2(gelu_erf(f1[mt][nt][2] + bq.x), gelu_erf(f1[mt][nt][3] + bq.y));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 5: ff.net.4 accumulated onto h + bias ----------------
+#pragma unroll
+    for (int nt = 0; nt < kFbNt; ++nt) {
+        const int c = col0 + nt * 8 + 2 * t;
+        const float2 bq = __ldg(reinterpret_cast<const float2*>(p.bf2 + c));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            acc[mt][nt][0] += bq.x; acc[mt][nt][1] += bq.y; acc[mt][nt][2] += bq.x; acc[mt][nt][3] += bq.y;
+        }
+    }
+    warp_stream_gemm<kFbNt, 32>(acc, static_cast<uint32_t>(__cvta_generic_to_shared(fs)), kFbFPitch * 2,
+                                p.w2 + static_cast<size_t>(col0) * kFbHid, kFbHid, kFbHid, ring, lane);
+
+    // ---------------- phase 6: norm2, store fp32 master + bf16 copy ----------------
+    layer_norm_tile(acc, p.g2, p.b2, col0, p.d, red + 4 * 8 * kFbRows, warp, lane);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+            const int r = mt * 16 + g + hi * 8;
+            if (r >= rows_valid) continue;
+            float* of = p.out_f32 + (out_row0 + r) * p.pitch;
+            bf16* ol = p.out_lp + (out_row0 + r) * p.pitch;
+#pragma unroll
+            for (int nt = 0; nt < kFbNt; ++nt) {
+                const int c = col0 + nt * 8 + 2 * t;
+                *reinterpret_cast<float2*>(of + c) = make_float2(acc[mt][nt][hi * 2], acc[mt][nt][hi * 2 + 1]);
+                *reinterpret_cast<uint32_t*>(ol + c) = pack_bf16x2(acc[mt][nt][hi * 2], acc[mt][nt][hi * 2 + 1]);
+            }
+        }
+}
+
+}  // namespace
+
+int fusion_block_launch(const FusionBlockParams& p, int batch, cudaStream_t s) {
+    if (batch == 0) return 0;
+    HMV_CHECK(p.pitch == kFbDp && p.d <= kFbDp && p.d % 2 == 0 && p.ld_qkv == 3 * kFbInner, "fusion block: d_model must be <= 576 (even) with 8 heads of 128");
+    HMV_CHECK(p.nq > 0 && p.nk > 0, "fusion block: empty attention");
+    static bool configured = false;
+    if (!configured) {
+        HMV_CUDA(cudaFuncSetAttribute(fusion_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmem));
+        configured = true;
+    }
+    HMV_CUDA(launch_kernel(fusion_block_kernel, dim3((p.nq + kFbRows - 1) / kFbRows, batch), dim3(256), kFbSmem, s, p));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace hmv

@@ -70,6 +70,28 @@ int layernorm_launch(const float* in, int ld_in, const float* g1, const float* b
                      const float* g2, const float* b2, T* out_lp, int ld_lp, int rows, int d, float eps,
                      cudaStream_t s);
 
+// One fusion-transformer layer after its QKV projection, fused (fusion_block.cu; reference layers.py:217-236):
+// attention -> to_out + residual -> norm1 -> ff (LayerNorm, Linear, GELU, Linear) + residual -> norm2.
+// All d_model-wide vectors / weight rows are zero padded to 576; bf16 tensor-core path only.
+struct FusionBlockParams {
+    const bf16* qkv;       // [batch * s_in, 3072]  (q | k | v, 8 heads x 128 each)
+    int ld_qkv;
+    const float* res_in;   // [batch * s_in, pitch] fp32 master copy of the layer input (residual)
+    int s_in, nq, nk, kv_row0;     // tokens per sample in; queries = tokens [0, nq); keys = tokens [kv_row0, kv_row0 + nk)
+    int pitch, d;
+    float scale_log2e;     // dim_head^-0.5 * log2(e)
+    const bf16* wo;        // [576, 1024]
+    const float* bo;       // [576]
+    const float *g1, *b1, *gff, *bff, *g2, *b2;   // LayerNorm affine, [576] each
+    const bf16* w1;        // [128, 576]
+    const float* bf1;      // [128]
+    const bf16* w2;        // [576, 128]
+    const float* bf2;      // [576]
+    float* out_f32;        // [batch * nq, pitch]
+    bf16* out_lp;          // [batch * nq, pitch]
+};
+int fusion_block_launch(const FusionBlockParams& p, int batch, cudaStream_t s);
+
 struct GcnParams {
     const float* x;        // [batch, 21, ld]
     int ld, d_in;

@@ -112,6 +112,9 @@ struct FusionLayerPlan {
     const float *g1, *b1, *gff, *bff, *g2, *b2;
     float *res_in, *out_f32;                      // token stream in / out (fp32 master)
     void *in_lp, *out_lp;
+    // bf16 path, fused layer kernel (fusion_block.cu): d_model-wide vectors / weight rows zero padded to the pitch
+    void *wo_p = nullptr, *w2_p = nullptr;
+    float *bo_p = nullptr, *b2_p = nullptr, *ln_p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace hmv
@@ -125,6 +128,7 @@ struct hmv_handle {
     int mb = 0, mb_img = 0, num_sms = 148, esz = 2;
     int fcap = 0;                                 // samples the fusion + graph-head stage handles per pass (>= mb)
     bool prepared = false;
+    bool fuse_block = true;                       // HMV_FUSION_UNFUSED=1: attention / projections / LayerNorms as separate kernels
     int64_t launches = 0;
     std::map<std::string, HostTensor> weights;
     std::vector<void*> allocs;
@@ -807,6 +811,24 @@ static int build_heads(hmv_handle* h) {
             if (upload_f32(h, &dg, g->data) || upload_f32(h, &db, b->data)) return 1;
             *gp[k] = dg; *bp[k] = db;
         }
+        if (h->bf16) {
+            const int P = h->pitch;
+            std::vector<float> wop(static_cast<size_t>(P) * 1024, 0.f), w2p(static_cast<size_t>(P) * 128, 0.f), bop(P, 0.f), b2p(P, 0.f);
+            HMV_CHECK(static_cast<int64_t>(wo->data.size()) == static_cast<int64_t>(h->d) * 1024 && static_cast<int64_t>(w2->data.size()) == static_cast<int64_t>(h->d) * 128,
+                      "unexpected to_out / ff.net.4 shape in " + p);
+            memcpy(wop.data(), wo->data.data(), wo->data.size() * sizeof(float));
+            memcpy(w2p.data(), w2->data.data(), w2->data.size() * sizeof(float));
+            memcpy(bop.data(), bo->data.data(), h->d * sizeof(float));
+            memcpy(b2p.data(), b2->data.data(), h->d * sizeof(float));
+            if (upload_weights(h, &fp.wo_p, wop) || upload_weights(h, &fp.w2_p, w2p) || upload_f32(h, &fp.bo_p, bop) || upload_f32(h, &fp.b2_p, b2p)) return 1;
+            for (int k = 0; k < 3; ++k) {
+                NEED(g, p + lnn[k] + ".weight"); NEED(b, p + lnn[k] + ".bias");
+                std::vector<float> gp2(P, 0.f), bp2(P, 0.f);
+                memcpy(gp2.data(), g->data.data(), h->d * sizeof(float));
+                memcpy(bp2.data(), b->data.data(), h->d * sizeof(float));
+                if (upload_f32(h, &fp.ln_p[2 * k], gp2) || upload_f32(h, &fp.ln_p[2 * k + 1], bp2)) return 1;
+            }
+        }
         fp.res_in = cur_f; fp.in_lp = cur_l; fp.out_f32 = nxt_f; fp.out_lp = nxt_l;
         h->fusion.push_back(fp);
         cur_f = nxt_f; cur_l = nxt_l;
@@ -888,6 +910,22 @@ static int run_fusion_t(hmv_handle* h, int n, cudaStream_t s) {
     for (auto& fp : h->fusion) {
         const int rows_in = n * fp.s_in, rows_q = n * fp.nq;
         if (run_layer(h, h->layers[fp.qkv], rows_in, s)) return 1;
+        if constexpr (sizeof(T) == 2) {
+            if (h->fuse_block && h->pitch == 576) {      // attention + to_out + residual + 3 LayerNorms + feed-forward in one kernel
+                FusionBlockParams q{};
+                q.qkv = static_cast<const bf16*>(h->qkvbuf); q.ld_qkv = 3072;
+                q.res_in = fp.res_in; q.s_in = fp.s_in; q.nq = fp.nq; q.nk = fp.nk; q.kv_row0 = fp.kv_row0;
+                q.pitch = h->pitch; q.d = h->d; q.scale_log2e = 0.08838834764831845f * 1.4426950408889634f;
+                q.wo = static_cast<const bf16*>(fp.wo_p); q.bo = fp.bo_p;
+                q.g1 = fp.ln_p[0]; q.b1 = fp.ln_p[1]; q.gff = fp.ln_p[2]; q.bff = fp.ln_p[3]; q.g2 = fp.ln_p[4]; q.b2 = fp.ln_p[5];
+                q.w1 = static_cast<const bf16*>(h->layers[fp.ff1].w); q.bf1 = h->layers[fp.ff1].bias;
+                q.w2 = static_cast<const bf16*>(fp.w2_p); q.bf2 = fp.b2_p;
+                q.out_f32 = fp.out_f32; q.out_lp = static_cast<bf16*>(fp.out_lp);
+                ++h->launches;
+                if (fusion_block_launch(q, n, s)) return 1;
+                continue;
+            }
+        }
         h->launches += 3;
         if constexpr (sizeof(T) == 2) {
             if (attention_mma_launch(static_cast<const bf16*>(h->qkvbuf), 3072, static_cast<bf16*>(h->attbuf), 1024, n, fp.s_in, 0,
@@ -1002,6 +1040,8 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     *h->err_flag_host = 0;
     if (h->bf16 && (hmv::tc_init() || hmv::bt_init())) { delete h; return 1; }
     {
+        const char* u = getenv("HMV_FUSION_UNFUSED");
+        h->fuse_block = !(u && u[0] == '1');
         const char* e = getenv("HMV_FUSE_TAIL");
         if (e && e[0] >= '0' && e[0] <= '7') h->fuse_mask = e[0] - '0';
     }
