@@ -1031,6 +1031,10 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     h->mb = cfg->micro_batch; h->mb_img = h->mb * h->V;
     h->fcap = h->mb >= 256 ? h->mb : (256 / h->mb) * h->mb;          // a multiple of the micro-batch
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("HMV_NUM_SMS")) {         // cap the persistent grids (two handles sharing one GPU on two streams)
+        const int v = atoi(e);
+        if (v >= 1 && v < h->num_sms) h->num_sms = v;
+    }
     if (cudaHostAlloc(reinterpret_cast<void**>(&h->err_flag_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_flag_dev), h->err_flag_host, 0) != cudaSuccess) {
         hmv::set_error("cannot allocate the mapped error flag");
