@@ -292,9 +292,10 @@ def run_own(args, lines):
                 "api": "HandMvNet.forward_host_async -> hmv_forward_host_async / hmv_host_wait (pinned host buffers, poses copied "
                        "back; at most 2 steps in flight); sync_call_ms = blocking HandMvNet.forward_host per call"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
+            "roofline": {"kernel": "conv_gemm_tc_kernel + bottleneck_tail_kernel (tcgen05 implicit-GEMM convs / linears, fused conv2+conv3 tails)",
+                         "bound": "tensor",
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops_sustained"], **tc_traffic(views, B, args.micro_batch),
                          "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                          "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps,
                          "kernel_share_of_step": (tc_ms / args.steps) / (dev_ms / args.steps),
@@ -310,6 +311,18 @@ def run_own(args, lines):
         lines.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def tc_traffic(views, batch, micro_batch):
+    """DRAM bytes (read + write) per launch of the dominant kernel class, from the committed ncu launch list of one
+    B=64 / 5-view step (profiles/r01/tc_traffic.json); null for any other workload."""
+    path = os.path.join(ROOT, "profiles", "r01", "tc_traffic.json")
+    if views != 5 or batch != 64 or micro_batch != 64 or not os.path.exists(path):
+        return {"traffic": None}
+    with open(path) as f:
+        t = json.load(f)
+    return {"traffic": t["tc_dram_bytes_per_launch_mean"], "traffic_unit": "bytes per launch (mean over the launches of a step)",
+            "traffic_per_step_bytes": t["tc_dram_bytes_per_step"], "traffic_source": t["source"]}
 
 
 def main():
