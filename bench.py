@@ -198,9 +198,10 @@ def run_own(args, lines):
         sampler.start()
     # clock ramp: a GPU coming out of idle needs ~1 s of load before it holds its boost clocks; this pre-warm is
     # not counted as one of the W warm-up steps
+    # (time-bounded, so the number of iterations differs between ranks: no collective inside this loop)
     t_ramp = time.perf_counter()
     while time.perf_counter() - t_ramp < args.ramp_seconds:
-        step()
+        model(x, bbox, cam)
         torch.cuda.synchronize(dev)
     for _ in range(args.warmup):
         step()
@@ -340,6 +341,9 @@ def main():
     ap.add_argument("--ramp-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("HMV_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["HMV_BENCH_WATCHDOG"]), exit=True)
     # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are pointed at stderr
     # for the duration of the run and the real stdout is restored for the final print.
     sys.stdout.flush()

@@ -325,3 +325,46 @@ def test_fused_stem_kernel(n_img):
     assert rel_l2(out, taps["maxpool"]) < 5e-3
     # every strip row and column is covered: no pooled pixel may be left at zero where the oracle is positive
     assert ((out == 0) & (taps["maxpool"] > 0.05)).float().mean() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# report: eager PyTorch on the same GPU (north star: "x the reference's eager PyTorch forward on 1 B200 at B=64")
+# ---------------------------------------------------------------------------------------------------
+def test_report_eager_torch_on_gpu():
+    """Times the oracle's backbone + pose_net (94 % of the model FLOPs; the remaining stages of the oracle build their
+    constants on the CPU) as plain eager PyTorch ON THE GPU at B=64 x 5 views - fp32 with TF32 convolutions and bf16
+    autocast, cudnn.benchmark on, i.e. an UPPER bound on what the reference's eager forward reaches on this device - next
+    to the product's full forward at the same batch.  Informational: prints the three numbers, asserts only sanity."""
+    views, b = 5, 64
+    m, ocfg, sd = build_pair(views, True, "bf16", micro_batch=64, seed=0)
+    sdg = {k: v.cuda() for k, v in sd.items()}
+    x, bbox, intr = O.make_inputs(b, views, seed=3)
+    xg, bg, ig = x.cuda(), bbox.cuda(), intr.cuda()
+    ximg = xg.reshape(-1, 3, 256, 256)
+    torch.backends.cudnn.benchmark = True
+
+    def eager():
+        return O.pose_net(sdg, O.backbone(sdg, ximg))
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        ms_fp32 = timed(eager, 5)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ms_bf16 = timed(eager, 5)
+        ms_own = timed(lambda: m(xg, bg, {"intrinsic": ig}), 10)
+    print(f"\n[eager-on-GPU report] B={b} x {views} views: oracle backbone+pose_net eager fp32/TF32 {ms_fp32:.1f} ms "
+          f"({b / ms_fp32 * 1e3:.0f} poses/s), eager bf16 autocast {ms_bf16:.1f} ms ({b / ms_bf16 * 1e3:.0f} poses/s); "
+          f"handmvnet_b200 full forward {ms_own:.2f} ms ({b / ms_own * 1e3:.0f} poses/s) -> "
+          f"{ms_fp32 / ms_own:.1f}x / {ms_bf16 / ms_own:.1f}x")
+    assert ms_own < ms_bf16
