@@ -21,8 +21,11 @@ int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, i
 
 // Fused bf16 stem: conv7x7/2 + BN + ReLU + maxpool3x3/2 straight from fp32 NCHW input (stem_pool.cu).
 // wpack: [7 taps][4 K-chunks][64 couts][8] bf16, element e of chunk kc = (pixel 2*kc + e/4, channel e%4).
-int stem_pool_launch(const float* x, const bf16* wpack, const float* bias, bf16* out, int n_img, int num_sms, int* err_flag,
-                     cudaStream_t s);
+// x: fp32 NCHW, or uint8 NCHW normalised on the fly with `norm` (ToTensor + Normalize of the reference data pipeline).
+struct StemNorm { float mean[3]; float std[3]; };
+int stem_pool_launch(const void* x, bool x_is_u8, const StemNorm& norm, const bf16* wpack, const float* bias, bf16* out, int n_img,
+                     int num_sms, int* err_flag, cudaStream_t s);
+int u8_to_f32_norm_launch(const uint8_t* in, float* out, size_t total, int hw, const StemNorm& norm, cudaStream_t s);
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC (reference resnet.py:165,221).
 template <typename T>

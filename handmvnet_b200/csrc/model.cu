@@ -149,6 +149,10 @@ struct hmv_handle {
     float* gcn_h1 = nullptr;
     void* stem_w = nullptr;                       // fused stem (bf16 path): packed weights + folded-BN bias
     float* stem_b = nullptr;
+    // uint8 inputs (hmv_forward_u8 / hmv_forward_host_u8_async): normalised inside the stem kernel
+    bool x_u8 = false;                            // element type of the x pointer of the call being enqueued
+    StemNorm norm{{0.485f, 0.456f, 0.406f}, {0.229f, 0.224f, 0.225f}};   // datasets/ho3d.py:35-40
+    float* u8_f32 = nullptr;                      // fp32 check mode: normalised copy of a uint8 micro-batch
     float* gcn_w[3] = {nullptr, nullptr, nullptr};
     float* gcn_b[3] = {nullptr, nullptr, nullptr};
     float *bbox_int = nullptr, *intr_int = nullptr;
@@ -173,6 +177,15 @@ struct hmv_handle {
     cudaEvent_t graph_in = nullptr, graph_out = nullptr;
     std::map<int, GraphSlot> graphs;
     int graph_max_batch = 0;                      // 0 = disabled
+    // Larger batches: a caller that runs the same buffers step after step (a benchmark / serving loop) gets a graph captured
+    // over ITS pointers (no staging copies): first sight of a pointer set runs eagerly, the second captures, later ones replay.
+    struct PtrGraph {
+        const void *x, *bbox, *intr; void *hm, *j2d, *j3d; int batch;
+        int seen; int kernels; cudaGraphExec_t exec; int64_t last_use;
+    };
+    std::vector<PtrGraph> ptr_graphs;
+    bool ptr_graphs_ok = true;
+    int64_t ptr_graph_clock = 0;
     float *g_x = nullptr, *g_bbox = nullptr, *g_intr = nullptr, *g_hm = nullptr, *g_xy = nullptr, *g_j = nullptr;
     // optional per-launch profiling of the tensor-core GEMM kernel (bench.py roofline leg)
     bool profiling = false;
@@ -860,11 +873,19 @@ static int run_backbone_t(hmv_handle* h, const float* x, int n_img, int num_step
         Step& st = h->backbone[i];
         if (st.kind == SK_PACK) {
             ++h->launches;
-            if (pack_input_launch<T>(x, static_cast<T*>(st.out), n_img, h->img, h->img, st.H, st.W, 3, s)) return 1;
+            const float* xf = x;
+            if (h->x_u8) {                            // fp32 check mode of the uint8 entry points: normalise first
+                const size_t total = static_cast<size_t>(n_img) * 3 * h->img * h->img;
+                if (!h->u8_f32 && dev_alloc_t(h, &h->u8_f32, static_cast<size_t>(h->mb_img) * 3 * h->img * h->img * sizeof(float), false)) return 1;
+                ++h->launches;
+                if (u8_to_f32_norm_launch(reinterpret_cast<const uint8_t*>(x), h->u8_f32, total, h->img * h->img, h->norm, s)) return 1;
+                xf = h->u8_f32;
+            }
+            if (pack_input_launch<T>(xf, static_cast<T*>(st.out), n_img, h->img, h->img, st.H, st.W, 3, s)) return 1;
         } else if (st.kind == SK_STEM_POOL) {
             ++h->launches;
-            if (stem_pool_launch(x, static_cast<const bf16*>(h->stem_w), h->stem_b, static_cast<bf16*>(st.out), n_img, h->num_sms,
-                                 h->err_flag_dev, s)) return 1;
+            if (stem_pool_launch(x, h->x_u8, h->norm, static_cast<const bf16*>(h->stem_w), h->stem_b, static_cast<bf16*>(st.out), n_img,
+                                 h->num_sms, h->err_flag_dev, s)) return 1;
         } else if (st.kind == SK_TAIL) {
             if (run_tail(h, st.layer, n_img, s)) return 1;
         } else if (st.kind == SK_MAXPOOL) {
@@ -1072,6 +1093,7 @@ int hmv_destroy(hmv_handle* h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
     for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& g : h->ptr_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->graph_in) cudaEventDestroy(h->graph_in);
     if (h->graph_out) cudaEventDestroy(h->graph_out);
@@ -1121,14 +1143,19 @@ int hmv_prepare(hmv_handle* h) {
     return 0;
 }
 
+// x advanced by `samples` samples (x is fp32, or uint8 when the call came through a *_u8 entry point)
+static inline const float* x_at(const hmv_handle* h, const float* x, size_t samples) {
+    const size_t per_sample = static_cast<size_t>(h->V) * 3 * h->img * h->img * (h->x_u8 ? 1 : sizeof(float));
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(x) + samples * per_sample);
+}
+
 static int forward_eager(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
                          float* joints_crop_img, float* joints_cam, cudaStream_t s) {
-    const size_t per_sample_x = static_cast<size_t>(h->V) * 3 * h->img * h->img;
     for (int p0 = 0; p0 < batch; p0 += h->fcap) {                     // fusion passes
         const int np = batch - p0 < h->fcap ? batch - p0 : h->fcap;
         for (int s0 = p0; s0 < p0 + np; s0 += h->mb) {                // backbone micro-batches
             const int n = p0 + np - s0 < h->mb ? p0 + np - s0 : h->mb;
-            if (hmv::run_front(h, x + s0 * per_sample_x, bbox ? bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
+            if (hmv::run_front(h, x_at(h, x, s0), bbox ? bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
                                intr ? intr + static_cast<size_t>(s0) * h->V * 4 : nullptr, n, s0 - p0,
                                heatmap ? heatmap + static_cast<size_t>(s0) * h->V * 21 * h->hm * h->hm : nullptr,
                                joints_crop_img ? joints_crop_img + static_cast<size_t>(s0) * h->V * 21 * 2 : nullptr, s))
@@ -1192,6 +1219,53 @@ static int forward_graph(hmv_handle* h, const float* x, const float* bbox, const
     return 0;
 }
 
+// Pointer-keyed graphs for batches above graph_max_batch (see hmv_handle::PtrGraph).
+static int forward_graph_ptr(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
+                             float* joints_crop_img, float* joints_cam, cudaStream_t user) {
+    constexpr size_t kMaxEntries = 8;
+    hmv_handle::PtrGraph* g = nullptr;
+    for (auto& e : h->ptr_graphs)
+        if (e.x == x && e.bbox == bbox && e.intr == intr && e.hm == heatmap && e.j2d == joints_crop_img && e.j3d == joints_cam && e.batch == batch) { g = &e; break; }
+    ++h->ptr_graph_clock;
+    if (!g) {                                          // first sight: remember the pointer set, run eagerly
+        if (h->ptr_graphs.size() >= kMaxEntries) {
+            size_t lru = 0;
+            for (size_t i = 1; i < h->ptr_graphs.size(); ++i) if (h->ptr_graphs[i].last_use < h->ptr_graphs[lru].last_use) lru = i;
+            if (h->ptr_graphs[lru].exec) cudaGraphExecDestroy(h->ptr_graphs[lru].exec);
+            h->ptr_graphs.erase(h->ptr_graphs.begin() + lru);
+        }
+        h->ptr_graphs.push_back({x, bbox, intr, heatmap, joints_crop_img, joints_cam, batch, 1, 0, nullptr, h->ptr_graph_clock});
+        return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, user);
+    }
+    g->last_use = h->ptr_graph_clock;
+    cudaStream_t s = h->graph_stream;
+    if (g->exec == nullptr) {                          // second sight: capture
+        cudaGraph_t graph = nullptr;
+        HMV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int64_t launches0 = h->launches;
+        const int rc = forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        g->kernels = static_cast<int>(h->launches - launches0);
+        h->launches = launches0;
+        if (rc == 0 && ce == cudaSuccess && graph != nullptr) ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != 0 || ce != cudaSuccess || g->exec == nullptr) {      // capture unsupported here: eager from now on
+            cudaGetLastError();
+            g->exec = nullptr;
+            h->ptr_graphs_ok = false;
+            if (rc != 0) return rc;
+            return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, user);
+        }
+    }
+    HMV_CUDA(cudaEventRecord(h->graph_in, user));
+    HMV_CUDA(cudaStreamWaitEvent(s, h->graph_in, 0));
+    HMV_CUDA(cudaGraphLaunch(g->exec, s));
+    h->launches += g->kernels;
+    HMV_CUDA(cudaEventRecord(h->graph_out, s));
+    HMV_CUDA(cudaStreamWaitEvent(user, h->graph_out, 0));
+    return 0;
+}
+
 int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
                 float* joints_crop_img, float* joints_cam, void* stream) {
     HMV_CHECK(h && h->prepared, "hmv_forward: handle not prepared");
@@ -1201,6 +1275,8 @@ int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* i
     if (hmv::check_flag(h)) return 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (batch > 0 && batch <= h->graph_max_batch && !h->profiling) return forward_graph(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    if (batch > 0 && h->graph_max_batch > 0 && h->ptr_graphs_ok && !h->profiling)
+        return forward_graph_ptr(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
     return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
 }
 
@@ -1241,7 +1317,7 @@ static int ensure_host_pipeline(hmv_handle* h, int batch) {
 // because the copy of their first chunk already overlaps the previous call.
 static int enqueue_host(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, float* heatmap,
                         float* joints_crop_img, float* joints_cam, bool ramp) {
-    const size_t per_sample_x = static_cast<size_t>(h->V) * 3 * h->img * h->img;
+    const size_t per_sample_bytes = static_cast<size_t>(h->V) * 3 * h->img * h->img * (h->x_u8 ? 1 : sizeof(float));
     const size_t nimg = static_cast<size_t>(batch) * h->V;
     cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
     if (h->cfg.use_crop) {
@@ -1258,7 +1334,7 @@ static int enqueue_host(hmv_handle* h, const float* x, const float* bbox, const 
             const int n = p0 + np - s0 < cap ? p0 + np - s0 : cap;
             const int b = static_cast<int>(h->chunk_seq & 1);
             if (h->chunk_seq >= 2) HMV_CUDA(cudaStreamWaitEvent(cs, h->ev_consumed[b], 0));
-            HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x + s0 * per_sample_x, per_sample_x * n * sizeof(float), cudaMemcpyHostToDevice, cs));
+            HMV_CUDA(cudaMemcpyAsync(h->xstage[b], x_at(h, x, s0), per_sample_bytes * n, cudaMemcpyHostToDevice, cs));
             HMV_CUDA(cudaEventRecord(h->ev_copied[b], cs));
             HMV_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[b], 0));
             if (hmv::run_front(h, h->xstage[b], h->cfg.use_crop ? h->d_bbox + static_cast<size_t>(s0) * h->V * 4 : nullptr,
@@ -1325,6 +1401,38 @@ int hmv_host_wait(hmv_handle* h, int64_t ticket) {
     HMV_CUDA(cudaEventSynchronize(h->ev_done[ticket % hmv_handle::kMaxInflight]));   // the stream is in-order: earlier tickets are done too
     h->tickets_waited = ticket + 1;
     return hmv::check_flag(h);
+}
+
+int hmv_set_input_norm(hmv_handle* h, const float* mean3, const float* std3) {
+    HMV_CHECK(h && mean3 && std3, "hmv_set_input_norm: null argument");
+    for (int c = 0; c < 3; ++c) {
+        HMV_CHECK(std3[c] > 0.f, "hmv_set_input_norm: std must be positive");
+        h->norm.mean[c] = mean3[c]; h->norm.std[c] = std3[c];
+    }
+    return 0;
+}
+
+int hmv_forward_u8(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
+                   float* joints_crop_img, float* joints_cam, void* stream) {
+    HMV_CHECK(h && h->prepared, "hmv_forward_u8: handle not prepared");
+    HMV_CHECK(batch >= 0, "negative batch");
+    HMV_CHECK(x || batch == 0, "hmv_forward_u8: x is null");
+    HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
+    if (hmv::check_flag(h)) return 1;
+    h->x_u8 = true;
+    const int rc = forward_eager(h, reinterpret_cast<const float*>(x), bbox, intr, batch, heatmap, joints_crop_img, joints_cam,
+                                 static_cast<cudaStream_t>(stream));
+    h->x_u8 = false;
+    return rc;
+}
+
+int hmv_forward_host_u8_async(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
+                              float* joints_crop_img, float* joints_cam, int64_t* ticket) {
+    HMV_CHECK(h, "hmv_forward_host_u8_async: null handle");
+    h->x_u8 = true;
+    const int rc = hmv_forward_host_async(h, reinterpret_cast<const float*>(x), bbox, intr, batch, heatmap, joints_crop_img, joints_cam, ticket);
+    h->x_u8 = false;
+    return rc;
 }
 
 int hmv_stage_run(hmv_handle* h, int32_t stage, const float* x, const float* bbox, const float* intr, int32_t batch,

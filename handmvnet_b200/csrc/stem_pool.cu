@@ -42,9 +42,12 @@ __device__ __forceinline__ uint4 max4(const uint4& a, const uint4& b) {
     return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
 }
 
+// U8 = true: x is uint8 NCHW and is normalised on the fly as ((v / 255) - mean[c]) / std[c] (torchvision ToTensor +
+// Normalize, reference datasets/ho3d.py:35-40), with the same IEEE operations in the same order as the host transform.
+template <bool U8>
 __global__ void __launch_bounds__(kStemThreads, 1)
-stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, const float* __restrict__ bias,
-                 bf16* __restrict__ out, int n_img, int* err_flag) {
+stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack, const float* __restrict__ bias,
+                 bf16* __restrict__ out, int n_img, int* err_flag, StemNorm norm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* wsm = smem;                                   // resident weights
@@ -97,7 +100,7 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
         for (int item = blockIdx.x; item < num_items && alive; item += gridDim.x) {
             const int n = item / (kPool / kStripPool), p0 = (item % (kPool / kStripPool)) * kStripPool;
             const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * kStripPool - 1;
-            const float* xn = x + static_cast<size_t>(n) * 3 * kImg * kImg;
+            const size_t img_off = static_cast<size_t>(n) * 3 * kImg * kImg;
             for (int j = c_lo; j <= c_hi + 3 && alive; ++j, ++gq) {              // pair j = padded rows 2j, 2j+1
                 if ((gq & 3) != static_cast<uint32_t>(warp)) continue;
                 const uint32_t slot = gq % kRingSlots;
@@ -106,13 +109,29 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
                 for (int rr = 0; rr < 2; ++rr) {
                     const int row = 2 * j + rr - 3;                              // original input row
                     const bool ok = row >= 0 && row < kImg;
-                    const float* pr = xn + static_cast<size_t>(ok ? row : 0) * kImg + 8 * lane;
+                    const size_t off = img_off + static_cast<size_t>(ok ? row : 0) * kImg + 8 * lane;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        if constexpr (U8) {
+                            uint2 q = make_uint2(0, 0);
+                            if (ok) q = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(x_raw) + off + ch * kImg * kImg));
+                            const float m = norm.mean[ch], sd = norm.std[ch];
+                            float f[8];
 #pragma unroll
-                        for (int hq = 0; hq < 2; ++hq)
-                            v[rr][ch][hq] = ok ? __ldg(reinterpret_cast<const float4*>(pr + ch * kImg * kImg) + hq)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int e = 0; e < 8; ++e) {
+                                const float b = static_cast<float>(((e < 4 ? q.x : q.y) >> (8 * (e & 3))) & 0xffu);
+                                f[e] = ok ? __fdiv_rn(__fsub_rn(__fdiv_rn(b, 255.f), m), sd) : 0.f;     // padding rows are zeros AFTER normalisation
+                            }
+                            v[rr][ch][0] = make_float4(f[0], f[1], f[2], f[3]);
+                            v[rr][ch][1] = make_float4(f[4], f[5], f[6], f[7]);
+                        } else {
+                            const float* pr = static_cast<const float*>(x_raw) + off;
+#pragma unroll
+                            for (int hq = 0; hq < 2; ++hq)
+                                v[rr][ch][hq] = ok ? __ldg(reinterpret_cast<const float4*>(pr + ch * kImg * kImg) + hq)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                 }
                 if (!mbar_wait(pempty0 + 8 * slot, ((gq / kRingSlots) & 1) ^ 1, err_flag, 11)) { alive = false; break; }
                 uint8_t* dst = ring + slot * kPairBytes;
@@ -253,17 +272,35 @@ stem_pool_kernel(const float* __restrict__ x, const bf16* __restrict__ wpack, co
 }  // namespace
 
 // wpack: [7 taps][4 K-chunks][64 couts][8 elements] bf16 with element e of chunk kc = (pixel kc*2 + e/4, channel e%4)
-int stem_pool_launch(const float* x, const bf16* wpack, const float* bias, bf16* out, int n_img, int num_sms, int* err_flag,
-                     cudaStream_t s) {
+int stem_pool_launch(const void* x, bool x_is_u8, const StemNorm& norm, const bf16* wpack, const float* bias, bf16* out, int n_img,
+                     int num_sms, int* err_flag, cudaStream_t s) {
     if (n_img == 0) return 0;
     static bool configured = false;
     if (!configured) {
-        HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
     const int items = n_img * (kPool / kStripPool);
-    HMV_CUDA(launch_kernel(stem_pool_kernel, dim3(items < num_sms ? items : num_sms), dim3(kStemThreads), kSmemBytes, s, x, wpack,
-                           bias, out, n_img, err_flag));
+    const dim3 grid(items < num_sms ? items : num_sms);
+    if (x_is_u8)
+        HMV_CUDA(launch_kernel(stem_pool_kernel<true>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm));
+    else
+        HMV_CUDA(launch_kernel(stem_pool_kernel<false>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm));
+    return 0;
+}
+
+// uint8 NCHW -> normalised fp32 NCHW (fp32 check mode of the uint8 entry points)
+__global__ void u8_to_f32_norm_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, size_t total, int hw, StemNorm norm) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = static_cast<int>((i / hw) % 3);
+    out[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(in[i]), 255.f), norm.mean[ch]), norm.std[ch]);
+}
+int u8_to_f32_norm_launch(const uint8_t* in, float* out, size_t total, int hw, const StemNorm& norm, cudaStream_t s) {
+    if (total == 0) return 0;
+    u8_to_f32_norm_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, total, hw, norm);
+    HMV_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -354,7 +354,8 @@ class HandMvNet(nn.Module):
         b, v, intr = self._check_inputs(x, bbox, cam_params)
         handle = self._ensure(x.device)
         dev = x.device
-        x = self._f32(x, dev)
+        u8 = x.dtype == torch.uint8                   # raw image bytes: ToTensor + Normalize run inside the stem kernel
+        x = x.contiguous() if u8 else self._f32(x, dev)
         crop = "crop" in self.pos_enc_list
         bbox_f = self._f32(bbox, dev) if crop else None
         intr_f = self._f32(intr, dev) if crop else None
@@ -363,8 +364,9 @@ class HandMvNet(nn.Module):
         j3d = torch.empty((b, NUM_JOINTS, 3), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(_lib.load().hmv_forward(handle, _lib.ptr(x), _lib.ptr(bbox_f), _lib.ptr(intr_f), b, _lib.ptr(hm),
-                                               _lib.ptr(j2d), _lib.ptr(j3d), stream), "hmv_forward")
+            fn = _lib.load().hmv_forward_u8 if u8 else _lib.load().hmv_forward
+            _lib.check(fn(handle, _lib.ptr(x), _lib.ptr(bbox_f), _lib.ptr(intr_f), b, _lib.ptr(hm),
+                          _lib.ptr(j2d), _lib.ptr(j3d), stream), "hmv_forward")
         return {"joints_crop_img": j2d, "joints_cam": j3d, "heatmap": hm}
 
     @torch.no_grad()
@@ -373,6 +375,8 @@ class HandMvNet(nn.Module):
         compute inside the library (hmv_forward_host); returns CPU tensors after completion."""
         if x.device.type != "cpu":
             raise ValueError("forward_host expects CPU tensors")
+        if x.dtype == torch.uint8:
+            return self.forward_host_async(x, bbox, cam_params, device, want_heatmap).result()
         b, v, intr = self._check_inputs(x, bbox, cam_params)
         if self._handle is None:
             self.prepare(device if device is not None else next(self.parameters()).device)
@@ -402,7 +406,8 @@ class HandMvNet(nn.Module):
         if self._handle is None:
             self.prepare(device if device is not None else next(self.parameters()).device)
         crop = "crop" in self.pos_enc_list
-        x = x.to(torch.float32).contiguous()
+        u8 = x.dtype == torch.uint8
+        x = x.contiguous() if u8 else x.to(torch.float32).contiguous()
         bbox_f = bbox.to(torch.float32).contiguous() if crop else None
         intr_f = intr.to(torch.float32).contiguous() if crop else None
         pool = self.__dict__.setdefault("_host_out_pool", {})
@@ -416,10 +421,16 @@ class HandMvNet(nn.Module):
             j2d = torch.empty((b, v, NUM_JOINTS, 2), dtype=torch.float32, pin_memory=pin)
             j3d = torch.empty((b, NUM_JOINTS, 3), dtype=torch.float32, pin_memory=pin)
         t = ctypes.c_int64(-1)
-        _lib.check(_lib.load().hmv_forward_host_async(self._handle, _lib.ptr(x), _lib.ptr(bbox_f), _lib.ptr(intr_f), b,
-                                                      _lib.ptr(hm), _lib.ptr(j2d), _lib.ptr(j3d), ctypes.byref(t)),
-                   "hmv_forward_host_async")
+        fn = _lib.load().hmv_forward_host_u8_async if u8 else _lib.load().hmv_forward_host_async
+        _lib.check(fn(self._handle, _lib.ptr(x), _lib.ptr(bbox_f), _lib.ptr(intr_f), b,
+                      _lib.ptr(hm), _lib.ptr(j2d), _lib.ptr(j3d), ctypes.byref(t)), "hmv_forward_host_async")
         return HostTicket(self, t.value, (x, bbox_f, intr_f), (hm, j2d, j3d), free)
+
+    def set_input_norm(self, mean, std):
+        """Per-channel mean / std applied to uint8 inputs (defaults: the reference's ImageNet constants, datasets/ho3d.py:35-40)."""
+        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+        _lib.check(_lib.load().hmv_set_input_norm(self._handle, m, sd), "hmv_set_input_norm")
 
     def synchronize(self):
         if self._handle is not None:

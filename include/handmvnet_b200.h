@@ -75,6 +75,18 @@ int hmv_forward_host_async(hmv_handle* h, const float* x, const float* bbox, con
                            float* heatmap, float* joints_crop_img, float* joints_cam, int64_t* ticket);
 int hmv_host_wait(hmv_handle* h, int64_t ticket);
 
+/* uint8 inputs: x is [B, V, 3, S, S] uint8 NCHW (what torchvision's ToTensor sees before its /255) and the stem kernel
+ * applies ((v / 255) - mean[c]) / std[c] on the fly - the ToTensor + Normalize step of the reference data pipeline
+ * (src/datasets/ho3d.py:35-40; defaults are its ImageNet constants) - so the host->device traffic of a batch drops 4x.
+ * Same IEEE operations in the same order as the host transform: results are bit-identical to hmv_forward on the
+ * host-normalised fp32 tensor.  hmv_forward_u8: device pointers, asynchronous on `stream`;
+ * hmv_forward_host_u8_async: host pointers, ticket semantics of hmv_forward_host_async. */
+int hmv_set_input_norm(hmv_handle* h, const float* mean3, const float* std3);
+int hmv_forward_u8(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch,
+                   float* heatmap, float* joints_crop_img, float* joints_cam, void* stream);
+int hmv_forward_host_u8_async(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch,
+                              float* heatmap, float* joints_crop_img, float* joints_cam, int64_t* ticket);
+
 /* Blocks until the handle's work is done and reports device-side pipeline errors. */
 int hmv_synchronize(hmv_handle* h);
 

@@ -327,6 +327,44 @@ def test_fused_stem_kernel(n_img):
     assert ((out == 0) & (taps["maxpool"] > 0.05)).float().mean() < 1e-4
 
 
+def test_uint8_input_and_graph_replay():
+    """uint8 images normalised inside the stem kernel must give bit-identical results to the host-side
+    ToTensor + Normalize (reference datasets/ho3d.py:35-40) fed through the fp32 entry points - device and host
+    (streaming) forms, both precisions; and a call repeated on the same buffers (captured into a CUDA graph on its
+    second sight, replayed afterwards) must keep returning the same values."""
+    views, b = 5, 3
+    g = torch.Generator().manual_seed(11)
+    xu = torch.randint(0, 256, (b, views, 3, 256, 256), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3, 1, 1)
+    xf = (xu.float().div(255) - mean) / std                      # ToTensor + Normalize
+    _, bbox, intr = O.make_inputs(b, views, seed=9)
+    for precision in ("bf16", "fp32"):
+        m, _, _ = build_pair(views, True, precision, micro_batch=2, seed=5)
+        want = _forward(m, xf, bbox, intr)
+        got = {k: v.cpu() for k, v in m(xu.cuda(), bbox.cuda(), {"intrinsic": intr.cuda()}).items()}
+        for k in want:
+            assert torch.equal(got[k], want[k]), f"{precision} device uint8 {k}"
+        h = m.forward_host(xu.pin_memory(), bbox.pin_memory(), {"intrinsic": intr.pin_memory()})
+        for k in want:
+            assert torch.equal(h[k], want[k]), f"{precision} host uint8 {k}"
+    # graph replay: same input buffers, outputs freed between calls so the allocator hands the same blocks back
+    m, _, _ = build_pair(views, True, "bf16", micro_batch=16, seed=5)
+    b2 = 12                                                        # above the small-batch graph limit
+    x2, bbox2, intr2 = O.make_inputs(b2, views, seed=13)
+    xg, bg, cg = x2.cuda(), bbox2.cuda(), {"intrinsic": intr2.cuda()}
+    n_before = m.launch_count()
+    first = {k: v.clone() for k, v in m(xg, bg, cg).items()}
+    per_forward = m.launch_count() - n_before
+    for _ in range(5):
+        out = m(xg, bg, cg)
+        for k in first:
+            assert torch.equal(out[k], first[k]), f"replay {k}"
+        del out
+    m.synchronize()
+    assert per_forward > 0 and m.launch_count() - n_before == 6 * per_forward      # replayed kernels are counted too
+
+
 # ---------------------------------------------------------------------------------------------------
 # report: eager PyTorch on the same GPU (north star: "x the reference's eager PyTorch forward on 1 B200 at B=64")
 # ---------------------------------------------------------------------------------------------------
