@@ -11,7 +11,7 @@ TENSOR = {"feat": 0, "heatmap": 1, "xy": 2, "tokens": 3, "fused": 4, "joints": 5
 
 # every symbol include/handmvnet_b200.h declares
 EXPORTS = ["hmv_create", "hmv_destroy", "hmv_set_weight", "hmv_prepare", "hmv_forward", "hmv_forward_host",
-           "hmv_forward_host_async", "hmv_host_wait", "hmv_set_input_norm", "hmv_forward_u8", "hmv_forward_host_u8_async",
+           "hmv_forward_host_async", "hmv_host_wait", "hmv_set_input_norm", "hmv_preprocess", "hmv_forward_u8", "hmv_forward_host_u8_async",
            "hmv_synchronize", "hmv_stage_run", "hmv_tensor_get", "hmv_tensor_set", "hmv_debug_backbone",
            "hmv_debug_num_steps", "hmv_debug_step_name", "hmv_conv_bn_act", "hmv_profile_enable", "hmv_profile_read", "hmv_profile_phases",
            "hmv_launch_count", "hmv_num_sms",
@@ -47,6 +47,7 @@ def load():
     lib.hmv_forward_host_async.argtypes = [vp, f32p, f32p, f32p, i32, f32p, f32p, f32p, ctypes.POINTER(i64)]
     lib.hmv_host_wait.argtypes = [vp, i64]
     lib.hmv_set_input_norm.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    lib.hmv_preprocess.argtypes = [vp, vp, vp, i32, i32, i32, f32p, vp]
     lib.hmv_forward_u8.argtypes = [vp, vp, f32p, f32p, i32, f32p, f32p, f32p, vp]
     lib.hmv_forward_host_u8_async.argtypes = [vp, vp, f32p, f32p, i32, f32p, f32p, f32p, ctypes.POINTER(i64)]
     lib.hmv_synchronize.argtypes = [vp]

@@ -787,4 +787,104 @@ int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Image transform in front of the model (reference datasets/utils.py:40-77 crop_and_pad_image, datasets/ho3d.py:35-40
+// ToTensor -> Resize((S, S), antialias=True) -> Normalize): full camera frames (uint8 HWC) + integer boxes ->
+// normalised fp32 NCHW crops.  The resize is torch's separable anti-aliased bilinear filter
+// (aten UpSampleKernel.cpp, _compute_indices_weights_aa): scale = in / out, support = max(scale, 1),
+// taps [int(c - support + .5), int(c + support + .5)) around c = scale * (i + .5), triangle weights normalised to 1;
+// horizontal pass first, then vertical, as the CPU kernel does.  One thread per output pixel.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kPreMaxTaps = 20;                 // crop side <= ~9 x the output side
+
+struct AaTaps { int lo, n; float w[kPreMaxTaps]; };
+
+__device__ __forceinline__ void aa_taps(int in_size, int out_size, int i, AaTaps& t, bool& overflow) {
+    const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+    const float support = scale >= 1.f ? scale : 1.f;
+    const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+    const float center = scale * (static_cast<float>(i) + 0.5f);
+    int lo = static_cast<int>(center - support + 0.5f);
+    lo = lo < 0 ? 0 : lo;
+    int hi = static_cast<int>(center + support + 0.5f);
+    hi = hi > in_size ? in_size : hi;
+    int n = hi - lo;
+    if (n > kPreMaxTaps) { n = kPreMaxTaps; overflow = true; }
+    float total = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPreMaxTaps; ++j) {
+        float w = 0.f;
+        if (j < n) {
+            const float x = fabsf((static_cast<float>(j + lo) - center + 0.5f) * invscale);
+            w = x < 1.f ? 1.f - x : 0.f;
+        }
+        t.w[j] = w;
+        total += w;
+    }
+    if (total != 0.f) {
+#pragma unroll
+        for (int j = 0; j < kPreMaxTaps; ++j) t.w[j] = t.w[j] / total;
+    }
+    t.lo = lo; t.n = n;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ bbox, float* __restrict__ out, int frame_h,
+                  int frame_w, int size, StemNorm norm, int* err_flag) {
+    pdl_wait();
+    const int n = blockIdx.y, oy = blockIdx.x;
+    const int x1 = bbox[4 * n], y1 = bbox[4 * n + 1], x2 = bbox[4 * n + 2], y2 = bbox[4 * n + 3];
+    const int cw = x2 - x1, ch = y2 - y1;
+    const uint8_t* img = frames + static_cast<size_t>(n) * frame_h * frame_w * 3;
+    bool overflow = cw <= 0 || ch <= 0;
+    AaTaps ty;
+    aa_taps(ch > 0 ? ch : 1, size, oy, ty, overflow);
+    for (int ox = threadIdx.x; ox < size; ox += blockDim.x) {
+        AaTaps tx;
+        aa_taps(cw > 0 ? cw : 1, size, ox, tx, overflow);
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int jy = 0; jy < ty.n; ++jy) {
+            const int fy = y1 + ty.lo + jy;                   // frame row of this crop row (outside the frame: zero padding)
+            float hacc[3] = {0.f, 0.f, 0.f};
+            if (fy >= 0 && fy < frame_h && !overflow) {
+                const uint8_t* row = img + static_cast<size_t>(fy) * frame_w * 3;
+#pragma unroll
+                for (int jx = 0; jx < kPreMaxTaps; ++jx) {
+                    if (jx < tx.n) {
+                        const int fx = x1 + tx.lo + jx;
+                        if (fx >= 0 && fx < frame_w) {
+                            const float w = tx.w[jx];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) hacc[c] += w * __fdiv_rn(static_cast<float>(row[fx * 3 + c]), 255.f);   // ToTensor
+                        }
+                    }
+                }
+            }
+            float wy = 0.f;
+#pragma unroll
+            for (int j = 0; j < kPreMaxTaps; ++j) wy = j == jy ? ty.w[j] : wy;      // register select (no local-memory indexing)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += wy * hacc[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[((static_cast<size_t>(n) * 3 + c) * size + oy) * size + ox] = __fdiv_rn(__fsub_rn(acc[c], norm.mean[c]), norm.std[c]);
+    }
+    if (overflow && threadIdx.x == 0) {
+        *reinterpret_cast<volatile int*>(err_flag) = 41;       // box empty or more than ~9x larger than the output
+        __threadfence_system();
+    }
+}
+
+int preprocess_launch(const uint8_t* frames, const int* bbox, float* out, int n_img, int frame_h, int frame_w, int size,
+                      const StemNorm& norm, int* err_flag, cudaStream_t s) {
+    if (n_img == 0) return 0;
+    HMV_CHECK(frame_h > 0 && frame_w > 0 && size > 0, "preprocess: bad geometry");
+    HMV_CUDA(launch_kernel(preprocess_kernel, dim3(size, n_img), dim3(256), 0, s, frames, bbox, out, frame_h, frame_w, size, norm, err_flag));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace hmv

@@ -25,6 +25,10 @@ int pack_input_launch(const float* x, T* out, int n_img, int H, int W, int Hp, i
 struct StemNorm { float mean[3]; float std[3]; };
 int stem_pool_launch(const void* x, bool x_is_u8, const StemNorm& norm, const bf16* wpack, const float* bias, bf16* out, int n_img,
                      int num_sms, int* err_flag, cudaStream_t s);
+// crop_and_pad_image + ToTensor + Resize(antialias) + Normalize (reference datasets/utils.py:40-77, ho3d.py:35-40):
+// frames [n, frame_h, frame_w, 3] uint8, bbox [n, 4] int32 xyxy -> out [n, 3, size, size] fp32
+int preprocess_launch(const uint8_t* frames, const int* bbox, float* out, int n_img, int frame_h, int frame_w, int size,
+                      const StemNorm& norm, int* err_flag, cudaStream_t s);
 int u8_to_f32_norm_launch(const uint8_t* in, float* out, size_t total, int hw, const StemNorm& norm, cudaStream_t s);
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC (reference resnet.py:165,221).

@@ -1011,7 +1011,8 @@ static int check_flag(hmv_handle* h) {
         const int code = *h->err_flag_host;
         *h->err_flag_host = 0;
         set_error("device pipeline timeout (role code " + std::to_string(code) +
-                  ": conv_gemm_tc 1=TMA producer, 2=MMA/tmem-empty, 3=MMA/smem-full, 4=epilogue, 5/6=residual ring; stem_pool 11-14)");
+                  ": conv_gemm_tc 1=TMA producer, 2=MMA/tmem-empty, 3=MMA/smem-full, 4=epilogue, 5/6=residual ring; stem_pool 11-14; "
+                  "bottleneck_tail 21-32; 41 = hmv_preprocess box empty or more than 9x the output size)");
         return 1;
     }
     return 0;
@@ -1410,6 +1411,16 @@ int hmv_set_input_norm(hmv_handle* h, const float* mean3, const float* std3) {
         h->norm.mean[c] = mean3[c]; h->norm.std[c] = std3[c];
     }
     return 0;
+}
+
+int hmv_preprocess(hmv_handle* h, const uint8_t* frames, const int32_t* bbox, int32_t n_img, int32_t frame_h, int32_t frame_w,
+                   float* x_out, void* stream) {
+    HMV_CHECK(h && h->prepared, "hmv_preprocess: handle not prepared");
+    HMV_CHECK(n_img >= 0 && (n_img == 0 || (frames && bbox && x_out)), "hmv_preprocess: bad argument");
+    if (hmv::check_flag(h)) return 1;
+    ++h->launches;
+    return hmv::preprocess_launch(frames, bbox, x_out, n_img, frame_h, frame_w, h->img, h->norm, h->err_flag_dev,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int hmv_forward_u8(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,

@@ -426,6 +426,34 @@ class HandMvNet(nn.Module):
                       _lib.ptr(hm), _lib.ptr(j2d), _lib.ptr(j3d), ctypes.byref(t)), "hmv_forward_host_async")
         return HostTicket(self, t.value, (x, bbox_f, intr_f), (hm, j2d, j3d), free)
 
+    @torch.no_grad()
+    def preprocess(self, frames, bbox):
+        """Camera frames [..., H, W, 3] uint8 (CUDA) + integer boxes [..., 4] xyxy -> normalised crops [..., 3, S, S] fp32:
+        the reference dataset's crop_and_pad_image + ToTensor + Resize(antialias) + Normalize (datasets/utils.py:40-77,
+        datasets/ho3d.py:35-40) as one kernel.  Feed the result to forward()."""
+        if frames.dtype != torch.uint8 or frames.dim() < 4 or frames.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [..., H, W, 3]")
+        if frames.device.type != "cuda":
+            raise RuntimeError("handmvnet_b200 has no CPU fallback: preprocess expects CUDA tensors")
+        lead = tuple(frames.shape[:-3])
+        hf, wf = int(frames.shape[-3]), int(frames.shape[-2])
+        n = 1
+        for d in lead:
+            n *= int(d)
+        if bbox.numel() != n * 4:
+            raise ValueError("bbox must hold one xyxy box per frame")
+        self._ensure(frames.device)
+        dev = frames.device
+        size = self.data_params.get("image_size", 256)
+        fr = frames.contiguous()
+        bb = bbox.to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty(lead + (3, size, size), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.load().hmv_preprocess(self._handle, _lib.ptr(fr), _lib.ptr(bb), n, hf, wf, _lib.ptr(out), stream),
+                       "hmv_preprocess")
+        return out
+
     def set_input_norm(self, mean, std):
         """Per-channel mean / std applied to uint8 inputs (defaults: the reference's ImageNet constants, datasets/ho3d.py:35-40)."""
         m = (ctypes.c_float * 3)(*[float(v) for v in mean])

@@ -82,6 +82,14 @@ int hmv_host_wait(hmv_handle* h, int64_t ticket);
  * host-normalised fp32 tensor.  hmv_forward_u8: device pointers, asynchronous on `stream`;
  * hmv_forward_host_u8_async: host pointers, ticket semantics of hmv_forward_host_async. */
 int hmv_set_input_norm(hmv_handle* h, const float* mean3, const float* std3);
+
+/* The image transform the reference's dataset applies in front of the model, on the device: crop_and_pad_image
+ * (src/datasets/utils.py:40-77; box parts outside the frame are zero) + ToTensor + Resize((S, S), antialias=True) +
+ * Normalize (src/datasets/ho3d.py:35-40, 139-147).  frames [n_img, frame_h, frame_w, 3] uint8 HWC, bbox [n_img, 4]
+ * int32 xyxy (x2 > x1, y2 > y1, side <= 9 * S), x_out [n_img, 3, S, S] fp32 - ready for hmv_forward.  Device
+ * pointers, asynchronous on `stream`; an invalid box is reported by the next call / hmv_synchronize. */
+int hmv_preprocess(hmv_handle* h, const uint8_t* frames, const int32_t* bbox, int32_t n_img, int32_t frame_h,
+                   int32_t frame_w, float* x_out, void* stream);
 int hmv_forward_u8(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch,
                    float* heatmap, float* joints_crop_img, float* joints_cam, void* stream);
 int hmv_forward_host_u8_async(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch,

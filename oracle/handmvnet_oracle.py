@@ -433,3 +433,55 @@ def forward(sd, cfg, x, bbox=None, intr=None, return_taps=False, teacher=None):
                     fused=fused, joints_cam=joints)
         return out, taps
     return out
+
+
+# ----------------------------------------------------------------------------
+# image transform in front of the model (reference src/datasets/ho3d.py:35-40, 139-147;
+# src/datasets/utils.py:40-77) - the caller side of the hot path
+# ----------------------------------------------------------------------------
+IMAGENET_MEAN = (0.485, 0.456, 0.406)       # ho3d.py:37-38
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def crop_and_pad_image(image: np.ndarray, bbox) -> np.ndarray:
+    """datasets/utils.py:40-77: crop [y1:y2, x1:x2] of an (h, w, 3) uint8 frame; parts of the box outside the frame
+    are zero."""
+    height, width = image.shape[:2]
+    x1, y1, x2, y2 = (int(v) for v in bbox)
+    sx, sy, ex, ey = max(0, x1), max(0, y1), min(width, x2), min(height, y2)
+    out = np.zeros((y2 - y1, x2 - x1, 3), dtype=np.uint8)
+    if ex > sx and ey > sy:
+        px, py = max(0, -x1), max(0, -y1)
+        out[py:py + (ey - sy), px:px + (ex - sx)] = image[sy:ey, sx:ex]
+    return out
+
+
+def image_transform(crop: np.ndarray, size: int = 256) -> torch.Tensor:
+    """ho3d.py:35-40 `img_transform`: ToTensor (HWC uint8 -> CHW float / 255), Resize((size, size), antialias=True)
+    (torchvision resizes tensors with F.interpolate(mode="bilinear", align_corners=False, antialias=True)), Normalize."""
+    t = torch.from_numpy(np.ascontiguousarray(crop)).permute(2, 0, 1).to(torch.float32).div(255)
+    t = F.interpolate(t[None], size=(size, size), mode="bilinear", align_corners=False, antialias=True)[0]
+    mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
+    return (t - mean) / std
+
+
+def preprocess(frames: np.ndarray, bboxes, size: int = 256) -> torch.Tensor:
+    """frames (n, h, w, 3) uint8, bboxes (n, 4) integer xyxy -> (n, 3, size, size) fp32: ho3d.py:139-147 for the
+    evaluation path (no augmentation; the all-joints-invisible black-image case is dataset logic, not arithmetic)."""
+    return torch.stack([image_transform(crop_and_pad_image(f, b), size) for f, b in zip(frames, bboxes)])
+
+
+def make_frames(n: int, seed: int = 0, height: int = 480, width: int = 640):
+    """Seeded synthetic camera frames + integer boxes covering: inside the frame, sticking out on every side,
+    smaller than the output (up-sampling), larger than it (anti-aliased down-sampling), non-square."""
+    g = torch.Generator().manual_seed(seed)
+    # smooth-ish content so that resampling errors are visible but values are not pure noise
+    base = torch.rand(n, 3, height // 8, width // 8, generator=g)
+    frames = F.interpolate(base, size=(height, width), mode="bilinear", align_corners=False)
+    frames = (frames + 0.15 * torch.rand(n, 3, height, width, generator=g)).clamp(0, 1)
+    frames = (frames * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy()
+    boxes = [(200, 120, 400, 320), (-40, -30, 180, 190), (500, 300, 700, 520), (60, 40, 580, 440),
+             (300, 200, 390, 290), (100, 50, 420, 300), (0, 0, 640, 480), (610, 450, 660, 500)]
+    bboxes = np.array([boxes[i % len(boxes)] for i in range(n)], dtype=np.int32)
+    return frames, bboxes

@@ -365,6 +365,33 @@ def test_uint8_input_and_graph_replay():
     assert per_forward > 0 and m.launch_count() - n_before == 6 * per_forward      # replayed kernels are counted too
 
 
+def test_preprocess_kernel_matches_oracle():
+    """hmv_preprocess (crop + pad + ToTensor + anti-aliased resize + Normalize in one kernel) against the oracle's
+    restatement of the reference transform (itself pinned by tests/golden/preprocess.npz): boxes inside the frame,
+    sticking out of it, up- and down-sampling, non-square.  fp32 arithmetic, different summation order: <= 1e-5 abs on
+    values of magnitude <= 2.7.  The crops then run through the model like any other input."""
+    m, _, _ = build_pair(5, True, "bf16", micro_batch=2, seed=5)
+    frames, bboxes = O.make_frames(10, seed=3)
+    want = O.preprocess(frames, bboxes)
+    fr = torch.from_numpy(frames).cuda().reshape(2, 5, 480, 640, 3)
+    got = m.preprocess(fr, torch.from_numpy(bboxes).cuda().reshape(2, 5, 4))
+    m.synchronize()
+    assert got.shape == (2, 5, 3, 256, 256)
+    err = (got.cpu().reshape(10, 3, 256, 256) - want).abs().max().item()
+    print(f"\npreprocess kernel vs oracle: max abs diff {err:.2e}")
+    assert err < 1e-5
+    _, bbox, intr = O.make_inputs(2, 5, seed=9)
+    out = m(got, bbox.cuda(), {"intrinsic": intr.cuda()})
+    ref = _forward(m, want.reshape(2, 5, 3, 256, 256), bbox, intr)
+    m.synchronize()
+    assert rel_l2(out["heatmap"], ref["heatmap"]) < 1e-2          # same crops up to 1e-5 -> same outputs within the bf16 stage tolerance
+    # an empty box is reported (device-side flag, surfaced by the next synchronising call)
+    bad = torch.tensor([[10, 10, 10, 20]], dtype=torch.int32).cuda()
+    m.preprocess(fr[0, :1], bad)
+    with pytest.raises(RuntimeError):
+        m.synchronize()
+
+
 # ---------------------------------------------------------------------------------------------------
 # report: eager PyTorch on the same GPU (north star: "x the reference's eager PyTorch forward on 1 B200 at B=64")
 # ---------------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ import torch
 import handmvnet_oracle as O
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(
-    os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("preprocess"))
 
 
 def _run(g):
@@ -87,3 +87,19 @@ def test_known_answers():
     cfg = O.release_config(5)
     with pytest.raises(ValueError):
         O.forward({}, cfg, torch.zeros(1, 8, 3, 256, 256))
+
+
+def test_preprocess_oracle_matches_reference_fixture(golden_dir):
+    """crop_and_pad_image + ToTensor + Resize(antialias) + Normalize: the oracle restatement against the fixture made by
+    oracle/gen_golden_preprocess.py with the reference's own crop function and torchvision's transforms."""
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    frames, bboxes = O.make_frames(8, seed=0)
+    np.testing.assert_array_equal(bboxes, g["bboxes"])
+    out = O.preprocess(frames, bboxes)
+    assert tuple(out.shape) == tuple(g["shape"])
+    np.testing.assert_allclose(out[:, :, ::8, ::8].numpy(), g["sub"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out.reshape(-1)[torch.from_numpy(g["idx"])].numpy(), g["val"], rtol=0, atol=1e-6)
+    assert abs(float(out.double().mean()) - float(g["mean"])) < 1e-6
+    # edge cases of the crop: a box entirely outside the frame is all zeros before normalisation
+    z = O.crop_and_pad_image(frames[0], (700, 500, 760, 560))
+    assert z.shape == (60, 60, 3) and not z.any()
