@@ -121,7 +121,9 @@ def test_fp32_end_to_end_matches_oracle(views, crop, seed):
 
 def test_fp32_matches_reference_golden_fixtures(golden_dir):
     """Directly against the fixtures the real reference produced (tests/golden, oracle/gen_golden.py)."""
-    for path in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+    paths = [p for p in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))) if not os.path.basename(p).startswith("preprocess")]
+    assert len(paths) >= 4
+    for path in paths:
         g = np.load(path)
         views, crop, b = int(g["meta_num_views"]), bool(g["meta_crop"]), int(g["meta_batch"])
         m, ocfg, sd = build_pair(views, crop, "fp32", micro_batch=b, seed=int(g["meta_seed_w"]),
