@@ -89,12 +89,18 @@ struct TcCfg {
     static_assert(kSmemBytes <= 227 * 1024 && kStages >= 2, "shared memory budget");
 };
 
-template <int BN, int MODE>
+// CL = 2: launched as clusters of two CTAs that work on two neighbouring M tiles of the same N tile at the same time.
+// Each CTA loads its own A tile and ONE HALF of the shared weight tile, multicast into both CTAs' shared memory
+// (tmB then has a BN/2-row box), which halves the L2 -> SM traffic of the B operand.  A stage may only be refilled when
+// BOTH CTAs have consumed it, so the MMA issuer's commit arrives on the `empty` barrier of both CTAs (count 2).
+template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, MODE>;
+    static_assert(CL == 1 || (CL == 2 && BN % 16 == 0), "cluster width");
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kCBytes);
@@ -120,7 +126,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) prefetch_tmap(&tmR);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, CL);                              // one commit per CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
@@ -140,12 +146,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything remote can land on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();                        // everything above overlapped the previous kernel; its results are visible from here
     pdl_launch_dependents();
 
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // Work items.  CL == 1: tile = (m_tile, n_tile), strided by the grid.  CL == 2: the cluster walks (pair of M tiles,
+    // n_tile) items and this CTA takes M tile 2 * pair + rank; an M tile past the end is a dummy (zero-filled loads,
+    // clipped stores) that still takes part in the stage hand-shake.
+    const int num_tiles = CL == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
+    const int tile0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto m_of = [&](int tile) { return CL == 2 ? 2 * (tile / p.num_n_tiles) + static_cast<int>(crank) : tile / p.num_n_tiles; };
     const int num_kb = p.num_taps * p.cblks;
 
     if (warp == 0) {
@@ -154,9 +167,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             bool alive = true;
-            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
                 const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = tile / p.num_n_tiles;
+                const int m_tile = m_of(tile);
                 const int w0 = p.flat ? m_tile * kTcBlockM : 0;
                 const int h0 = p.flat ? 0 : (m_tile % p.tpi) * p.hbox;
                 const int img = p.flat ? 0 : m_tile / p.tpi;
@@ -169,7 +182,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                         mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
                         tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
-                        tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
+                        if (CL == 2)       // this CTA's half of the weight tile, delivered to both CTAs
+                            tma_load_2d_mc(sa + Cfg::kABytes + crank * (Cfg::kBBytes / 2), &tmB, fb, kb * kTcBlockK,
+                                           n_tile * BN + static_cast<int>(crank) * (BN / 2), static_cast<uint16_t>(3));
+                        else
+                            tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -185,7 +202,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int acc = 0;
             uint32_t acc_phase = 0;
             bool alive = true;
-            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
                 if (!mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, p.err_flag, 2)) { alive = false; break; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -200,7 +217,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t bdesc = make_sw128_desc(sb + k * kTcUmmaK * 2);
                         umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
+                    if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));   // both CTAs' producers wait for both consumers
+                    else umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (!alive) break;
@@ -215,9 +233,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (MODE == TC_STORE_RES && has_res && lane == 0) {
             uint32_t g = 0;
             bool alive = true;
-            for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
                 const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = tile / p.num_n_tiles;
+                const int m_tile = m_of(tile);
                 for (int c = 0; c < BN / kChunkCols; ++c, ++g) {
                     constexpr uint32_t R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
                     const uint32_t slot = g % R, use = g / R;
@@ -234,9 +252,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = tile / p.num_n_tiles;
+            const int m_tile = m_of(tile);
             if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) break;
             tc_fence_after();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -277,9 +295,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t acc_phase = 0;
         bool alive = true;
         uint32_t g = 0;                                    // running chunk counter
-        for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = tile / p.num_n_tiles;
+            const int m_tile = m_of(tile);
             if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) { alive = false; break; }
             tc_fence_after();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 32;
@@ -352,6 +370,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -370,8 +389,11 @@ static EncodeTiledFn g_encode = nullptr;
 
 template <int BN, int MODE>
 static int set_attr() {
-    HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcCfg<BN, MODE>::kSmemBytes));
+    if (BN == 256)
+        HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE, BN == 256 ? 2 : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<BN, MODE>::kSmemBytes));
     return 0;
 }
 
@@ -445,9 +467,32 @@ int tc_pick_bn(int n) {
 
 template <int BN, int MODE>
 static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
+    if constexpr (BN == 256) {
+        if (l.cluster == 2) {          // pairs of CTAs sharing multicast weight tiles (l.tmB has a BN/2-row box)
+            // the persistent grid must be co-resident: clusters are placed inside one GPC, so fewer than num_sms / 2 may fit
+            static int max_clusters = -1;
+            if (max_clusters < 0) {
+                cudaLaunchConfig_t qc{};
+                qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = TcCfg<BN, MODE>::kSmemBytes;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa; qc.numAttrs = 1;
+                int n = 0;
+                HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_kernel<BN, MODE, 2>, &qc));
+                HMV_CHECK(n > 0, "no 2-CTA cluster of the conv kernel fits on this device");
+                max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+            }
+            const int items = ((l.p.num_m_tiles + 1) / 2) * l.p.num_n_tiles;
+            const int clusters = items < max_clusters ? items : max_clusters;
+            HMV_CUDA(launch_kernel_cluster(conv_gemm_tc_kernel<BN, MODE, 2>, dim3(2 * clusters), dim3(kTcThreads), 2,
+                                           TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB, l.tmC, l.tmR, l.p));
+            return 0;
+        }
+    }
     const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    HMV_CUDA(launch_kernel(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(kTcThreads), TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB,
+    HMV_CUDA(launch_kernel(conv_gemm_tc_kernel<BN, MODE, 1>, dim3(grid), dim3(kTcThreads), TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB,
                            l.tmC, l.tmR, l.p));
     return 0;
 }

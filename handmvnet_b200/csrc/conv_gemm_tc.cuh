@@ -53,6 +53,7 @@ struct TcLaunch {                      // everything needed to enqueue one layer
     TcParams p;
     int bn;
     int mode;
+    int cluster;                       // 1, or 2: CTA pairs with multicast weight tiles (BN = 256 only; tmB box is BN/2 rows)
 };
 
 // Host API -------------------------------------------------------------------------------------

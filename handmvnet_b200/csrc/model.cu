@@ -18,6 +18,10 @@ namespace hmv {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
+bool clusters_enabled() {
+    static const bool on = [] { const char* e = getenv("HMV_CLUSTER"); return !(e && e[0] == '0'); }();
+    return on;
+}
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("HMV_NO_PDL"); return !(e && e[0] == '1'); }();
     return on;
@@ -128,6 +132,7 @@ struct hmv_handle {
     int mb = 0, mb_img = 0, num_sms = 148, esz = 2;
     int fcap = 0;                                 // samples the fusion + graph-head stage handles per pass (>= mb)
     bool prepared = false;
+    bool use_clusters = hmv::clusters_enabled();  // HMV_CLUSTER=0: no CTA pairs / multicast weight tiles
     bool fuse_block = true;                       // HMV_FUSION_UNFUSED=1: attention / projections / LayerNorms as separate kernels
     int64_t launches = 0;
     std::map<std::string, HostTensor> weights;
@@ -352,7 +357,9 @@ static int build_tc(hmv_handle* h, Layer& L) {
         set_error(std::string(get_error()) + " [A map of " + L.name + "]");
         return 1;
     }
-    if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, L.bn)) {
+    // wide, K-deep layers run as 2-CTA clusters that share multicast weight tiles (conv_gemm_tc.cu, CL = 2)
+    t.cluster = (L.bn == 256 && L.K >= 512 && h->use_clusters) ? 2 : 1;
+    if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster == 2 ? L.bn / 2 : L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
         return 1;
     }
@@ -569,7 +576,8 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
     BtLaunch& b = T.bt;
     memset(&b.p, 0, sizeof(b.p));
     b.planes = P;
-    b.tmA = A.tc.tmA; b.tmW2 = A.tc.tmB; b.tmY2s = A.tc.tmC;
+    b.tmA = A.tc.tmA; b.tmY2s = A.tc.tmC;
+    if (tc_make_tmap_wgt(&b.tmW2, A.w, A.K, A.n_alloc, P)) return 1;        // full-height box (the layer's own map may be a half box)
     b.tmOut = B.tc.tmC; b.tmRes = B.tc.tmR;
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
     if (tc_make_tmap_out(&b.tmY2l, A.ep.out, P, rows, 128) || tc_make_tmap_out(&b.tmW3, B.w, P, 4 * P, 128)) {
