@@ -348,7 +348,7 @@ def tc_traffic(views, batch, micro_batch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=64, help="samples per internal pass")
