@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhandmvnet_b200.so")
-SOURCES = ["conv_gemm_tc.cu", "bottleneck_tc.cu", "stem_pool.cu", "conv_f32.cu", "head_kernels.cu", "fusion_block.cu", "model.cu"]
+SOURCES = ["conv_gemm_tc.cu", "bottleneck_tc.cu", "bottleneck_next_tc.cu", "stem_pool.cu", "conv_f32.cu", "head_kernels.cu", "fusion_block.cu", "model.cu"]
 HEADERS = ["common.cuh", "conv_gemm_tc.cuh", "tc_ptx.cuh", "kernels.cuh", os.path.join("..", "..", "include", "handmvnet_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]

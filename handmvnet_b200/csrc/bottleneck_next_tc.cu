@@ -1,0 +1,336 @@
+// Fused bottleneck seam for layer3 (P = 256): conv3 1x1 (+BN) + residual + ReLU of block b  ->  conv1 1x1 (+BN) + ReLU
+// of block b+1, in ONE persistent tcgen05 kernel (reference backbones/resnet.py:135-143 followed by :127-129 of the
+// next Bottleneck).
+//
+// Why: both layers are HBM-bound as separate kernels (conv3 writes the 1024-channel block output and re-reads the
+// 1024-channel residual, conv1 reads the block output again).  Here the block output tile is produced in shared
+// memory, TMA-stored once, and consumed from shared memory as the A operand of the next conv1 - the 671 MB re-read of a
+// B=64 pass disappears and conv1's tensor work hides under conv3's residual / store traffic.
+//
+//   per M tile (128 pixels), MMA issue order (one thread):
+//     T3(0) T3(1) T1(0) T3(2) T1(1) ... T3(7) T1(6) T1(7)
+//     T3(c): acc3[c & 1][128 x 128] = Y2[m] * W3[c]^T            (K = 256 = 4 K blocks: A and W3 chunk through the ring)
+//     T1(c): acc1[128 x 256]      += OUT[m, chunk c] * W1[:, chunk c]^T   (2 K blocks; A = the two staging slots of
+//                                                                   chunk c, B = W1 K block through the ring)
+//   epilogue (8 warps), in the same order: E3(c) = TMEM -> +bias3 +residual -> ReLU -> bf16 IN PLACE in the slot the
+//   residual was prefetched into (128B swizzle = the canonical K-major A operand layout) -> TMA store of the block output
+//   + "A ready" to the MMA issuer;  E1 = acc1 -> +bias1 -> ReLU -> bf16 -> TMA store of the next block's conv1 output.
+//   A slot is recycled when the TMA store has read it AND the T1 MMAs that use it have retired.
+//   TMEM: acc1 at columns [0, 256), acc3 double-buffered at 256 / 384.   Shared memory: 4 operand stages of 32 KiB
+//   and 6 chunk slots of 16 KiB.
+#include "conv_gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace hmv {
+
+namespace {
+
+constexpr int kBnP = 256;                                       // planes: K of conv3, N of the next conv1
+constexpr int kBnN3 = 4 * kBnP;                                 // block output channels
+constexpr int kBnChunk = 128;                                   // conv3 output columns per T3
+constexpr int kBnNch = kBnN3 / kBnChunk;                        // 8 chunks per tile
+constexpr int kBnKb3 = kBnP / kTcBlockK;                        // 4 K blocks per T3
+constexpr int kBnSlotCols = 64;
+constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
+constexpr int kBnSlots = 6;
+constexpr int kBnStageBytes = 32 * 1024;                        // T3: A 16 KiB + W3 chunk 16 KiB; T1: W1 K block 32 KiB
+constexpr int kBnStages = 4;
+constexpr int kBnSlotsPerTile = 2 * kBnNch + kBnP / kBnSlotCols; // 16 conv3 slots + 4 conv1 slots
+constexpr int kBnSmemBytes = kBnStages * kBnStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(kBnSmemBytes <= 227 * 1024, "shared memory budget");
+
+template <typename F3, typename F1>
+__device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
+    for (int c = 0; c < kBnNch; ++c) {
+        if (!t3(c)) return false;
+        if (c >= 1 && !t1(c - 1)) return false;
+    }
+    return t1(kBnNch - 1);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 output [rows, 256], load box {64, 128}
+                       const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}
+                       const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 1024], load box {64, 128}
+                       const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 32}
+                       const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}
+                       const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
+                       const __grid_constant__ BnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* slots = smem + kBnStages * kBnStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slots + kBnSlots * kBnSlotBytes);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * kBnStages;
+    const uint32_t t3full0 = empty0 + 8 * kBnStages;
+    const uint32_t t3empty0 = t3full0 + 16;
+    const uint32_t t1full = t3empty0 + 16;
+    const uint32_t t1empty = t1full + 8;
+    const uint32_t sres0 = t1empty + 8;                       // [slots] residual landed / slot handed to the epilogue
+    const uint32_t aready0 = sres0 + 8 * kBnSlots;            // [slots] finished block-output chunk is in the slot
+    const uint32_t sfree0 = aready0 + 8 * kBnSlots;           // [slots] store has read the slot and its MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBnStages + 6 + 3 * kBnSlots);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t slots_base = smem_u32(slots);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmY2); prefetch_tmap(&tmW3); prefetch_tmap(&tmRes); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmY1);
+        for (int i = 0; i < kBnStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(t3full0 + 8 * i, 1);
+            mbar_init(t3empty0 + 8 * i, 8);                 // one arrival per epilogue warp
+        }
+        mbar_init(t1full, 1);
+        mbar_init(t1empty, 8);
+        for (int i = 0; i < kBnSlots; ++i) {
+            mbar_init(sres0 + 8 * i, 1);
+            mbar_init(aready0 + 8 * i, 8);
+            mbar_init(sfree0 + 8 * i, 5);                   // 4 slab-store issuers + the MMA commit (conv3 slots) / the slot producer (conv1 slots)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    pdl_wait();
+    pdl_launch_dependents();
+
+    const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+
+    if (warp == 0) {
+        // ===================== TMA producer of the operand ring (same order as the MMA issuer consumes it) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_i; ++i) {
+                const int m = tile_of(i);
+                const bool ok = bn_tile_schedule(
+                    [&](int c) {
+                        for (int kb = 0; kb < kBnKb3; ++kb) {
+                            if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51)) return false;
+                            const uint32_t fb = full0 + 8 * stage;
+                            const uint32_t sa = smem_base + stage * kBnStageBytes;
+                            mbar_arrive_expect_tx(fb, kBnStageBytes);
+                            tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
+                            tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            if (++stage == kBnStages) { stage = 0; phase ^= 1; }
+                        }
+                        return true;
+                    },
+                    [&](int c) {
+                        for (int j = 0; j < 2; ++j) {
+                            if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52)) return false;
+                            const uint32_t fb = full0 + 8 * stage;
+                            mbar_arrive_expect_tx(fb, kBnStageBytes);
+                            tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            if (++stage == kBnStages) { stage = 0; phase ^= 1; }
+                        }
+                        return true;
+                    });
+                if (!ok) break;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc3 = make_idesc(kBnChunk);
+            constexpr uint32_t idesc1 = make_idesc(kBnP);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t q3 = 0;                                 // running conv3 chunk counter (TMEM slot = q3 & 1)
+            for (int i = 0; i < n_i; ++i) {
+                const uint32_t gbase = static_cast<uint32_t>(i) * kBnSlotsPerTile;
+                const bool ok = bn_tile_schedule(
+                    [&](int) {
+                        const uint32_t s = q3 & 1u, use = q3 >> 1;
+                        if (!mbar_wait(t3empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 53)) return false;
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + kBnP + s * kBnChunk;
+                        for (int kb = 0; kb < kBnKb3; ++kb) {
+                            if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 54)) return false;
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * kBnStageBytes;
+                            const uint32_t sb = sa + kBnStageBytes / 2;
+#pragma unroll
+                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                                umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
+                                         (kb | k) != 0 ? 1u : 0u);
+                            umma_commit(empty0 + 8 * stage);
+                            if (++stage == kBnStages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(t3full0 + 8 * s);
+                        ++q3;
+                        return true;
+                    },
+                    [&](int c) {
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t g = gbase + 2 * c + j, slot = g % kBnSlots, use = g / kBnSlots;
+                            if (c == 0 && j == 0) {          // acc1 drained by the epilogue of the previous tile
+                                if (!mbar_wait(t1empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, p.err_flag, 55)) return false;
+                            }
+                            if (!mbar_wait(aready0 + 8 * slot, use & 1u, p.err_flag, 56)) return false;
+                            if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 57)) return false;
+                            tc_fence_after();
+                            const uint32_t sa = slots_base + slot * kBnSlotBytes;          // finished block-output chunk = A operand
+                            const uint32_t sb = smem_base + stage * kBnStageBytes;
+#pragma unroll
+                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                                umma_f16(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
+                                         (c | j | k) != 0 ? 1u : 0u);
+                            umma_commit(empty0 + 8 * stage);
+                            umma_commit(sfree0 + 8 * slot);                                // the slot's MMAs have retired
+                            if (++stage == kBnStages) { stage = 0; phase ^= 1; }
+                        }
+                        if (c == kBnNch - 1) umma_commit(t1full);
+                        return true;
+                    });
+                if (!ok) break;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===================== slot producer: residual prefetch (conv3 slots) / plain hand-over (conv1 slots) =====================
+        if (lane == 0) {
+            uint32_t g = 0;
+            bool alive = true;
+            for (int i = 0; i < n_i && alive; ++i) {
+                const int m = tile_of(i);
+                for (int c = 0; c < kBnSlotsPerTile && alive; ++c, ++g) {
+                    const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
+                    if (!mbar_wait(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58)) { alive = false; break; }
+                    if (c < 2 * kBnNch) {
+                        mbar_arrive_expect_tx(sres0 + 8 * slot, kBnSlotBytes);
+                        tma_load_2d(slots_base + slot * kBnSlotBytes, &tmRes, sres0 + 8 * slot, c * kBnSlotCols, m * kTcBlockM);
+                    } else {
+                        mbar_arrive(sres0 + 8 * slot);
+                        mbar_arrive(sfree0 + 8 * slot);      // stands in for the MMA commit: conv1 slots feed no MMA
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of a 64-column slot =====================
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const bool issuer = half == 0 && lane == 0;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
+        const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
+        uint32_t g = 0;
+        int pending = -1;                                    // issuer: slot whose TMA store may still be reading smem
+        bool alive = true;
+
+        auto do_slot = [&](uint32_t tcol, const float* bias, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
+            const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
+            uint32_t r[32];
+            tmem_ld32(lane_base + tcol, r);
+            float4 bq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + j);
+            if (!mbar_wait(sres0 + 8 * slot, use & 1u, p.err_flag, 59)) alive = false;
+            uint8_t* srow = slots + slot * kBnSlotBytes + slab_off;
+            uint4 rq[4];
+            if (is_conv3) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
+            }
+            tmem_ld_wait();
+            if (release_bar != 0) {                          // accumulator fully read: hand TMEM back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(release_bar);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
+                float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
+                float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
+                float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                if (is_conv3) {
+                    v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
+                    v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+                }
+                uint4 o;
+                o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
+                o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
+                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4)) = o;
+            }
+            fence_async_smem();                              // generic-proxy writes -> visible to the TMA store and to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready0 + 8 * slot);  // every slot use (conv1 slots too: keeps the barrier's phase == use count)
+            named_bar_sync(1 + quarter, 64);                 // both column halves of this quarter's slab are written
+            if (issuer) {
+                tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
+                bulk_commit();
+                if (pending >= 0) {                          // the previous store has left shared memory
+                    bulk_wait_read<1>();
+                    mbar_arrive(sfree0 + 8 * pending);
+                }
+                pending = static_cast<int>(slot);
+            }
+            ++g;
+        };
+
+        uint32_t q3 = 0;
+        for (int i = 0; i < n_i && alive; ++i) {
+            const int m = tile_of(i);
+            for (int c = 0; c < kBnNch && alive; ++c, ++q3) {
+                const uint32_t s = q3 & 1u;
+                if (!mbar_wait(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60)) { alive = false; break; }
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < 2 && alive; ++cc)
+                    do_slot(kBnP + s * kBnChunk + cc * kBnSlotCols, p.bias3 + c * kBnChunk + cc * kBnSlotCols, true,
+                            cc == 1 ? t3empty0 + 8 * s : 0u, &tmOut, c * kBnChunk + cc * kBnSlotCols, m * kTcBlockM);
+            }
+            if (!alive) break;
+            if (!mbar_wait(t1full, static_cast<uint32_t>(i) & 1u, p.err_flag, 61)) { alive = false; break; }
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < kBnP / kBnSlotCols && alive; ++cc)
+                do_slot(cc * kBnSlotCols, p.bias1 + cc * kBnSlotCols, false, cc == kBnP / kBnSlotCols - 1 ? t1empty : 0u, &tmY1,
+                        cc * kBnSlotCols, m * kTcBlockM);
+        }
+        if (issuer) bulk_wait_read<0>();                     // staged data must stay valid until every store has read it
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+int bn_init() {
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    return 0;
+}
+
+int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
+    if (l.p.num_m_tiles <= 0) return 0;
+    const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
+    HMV_CUDA(launch_kernel(bottleneck_next_kernel, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
+                           l.tmW1, l.tmY1, l.p));
+    return 0;
+}
+
+}  // namespace hmv

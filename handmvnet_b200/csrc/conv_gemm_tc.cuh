@@ -84,4 +84,18 @@ struct BtLaunch {
 int bt_init();                                               // shared-memory attributes of the three instantiations
 int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream);
 
+// ---- fused bottleneck seam (bottleneck_next_tc.cu): conv3 + residual + ReLU of block b -> conv1 + ReLU of block b+1 (P = 256) ----
+struct BnParams {
+    int num_m_tiles;
+    const float* bias3;                // [1024] folded BN of conv3 (block b)
+    const float* bias1;                // [256]  folded BN of conv1 (block b+1)
+    int* err_flag;
+};
+struct BnLaunch {
+    CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;
+    BnParams p;
+};
+int bn_init();
+int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream);
+
 }  // namespace hmv

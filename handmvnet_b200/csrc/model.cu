@@ -93,7 +93,7 @@ struct HostTensor {
     std::vector<int64_t> dims;
 };
 
-enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4 };
+enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4, SK_SEAM = 5 };
 struct Step {
     int kind;
     std::string name;
@@ -108,6 +108,13 @@ struct FusedTail {
     std::string name;
     int l2 = -1, l3 = -1;                         // the two layers it covers (weights, biases, maps live there)
     BtLaunch bt{};
+};
+
+// conv3 (+residual) of block b + conv1 of block b+1 as a single launch (bottleneck_next_tc.cu, layer3 only)
+struct FusedSeam {
+    std::string name;
+    int l3 = -1, l1 = -1;
+    BnLaunch bn{};
 };
 
 struct FusionLayerPlan {
@@ -140,6 +147,8 @@ struct hmv_handle {
     std::vector<Layer> layers;
     std::vector<Step> backbone;
     std::vector<FusedTail> tails;
+    std::vector<FusedSeam> seams;
+    bool fuse_next = false;                       // HMV_FUSE_NEXT=1: layer3 conv3(b) + conv1(b+1) in one kernel
     int fuse_mask = 3;                            // bottleneck widths whose conv2+conv3 run fused: bit0 P=64, bit1 P=128, bit2 P=256 (HMV_FUSE_TAIL=<mask>)
     std::vector<FusionLayerPlan> fusion;
     int pose0 = -1, pose3 = -1, samp = -1;
@@ -194,7 +203,7 @@ struct hmv_handle {
     float *g_x = nullptr, *g_bbox = nullptr, *g_intr = nullptr, *g_hm = nullptr, *g_xy = nullptr, *g_j = nullptr;
     // optional per-launch profiling of the tensor-core GEMM kernel (bench.py roofline leg)
     bool profiling = false;
-    struct ProfRec { int layer; int units; cudaEvent_t e0, e1; int tail; };   // tail >= 0: fused conv2+conv3 launch
+    struct ProfRec { int layer; int units; cudaEvent_t e0, e1; int tail; int seam = -1; };   // tail / seam >= 0: fused launches
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase id, event) recorded while profiling
@@ -469,6 +478,30 @@ static int run_tail(hmv_handle* h, int tail, int units, cudaStream_t s) {
     return rc;
 }
 
+// Enqueue a fused conv3(b) + conv1(b+1) seam for `units` images.
+static int run_seam(hmv_handle* h, int seam, int units, cudaStream_t s) {
+    FusedSeam& S = h->seams[seam];
+    if (units == 0) return 0;
+    const Layer& L3 = h->layers[S.l3];
+    HMV_CHECK(units <= L3.max_units, "run_seam: batch exceeds the workspace of " + S.name);
+    ++h->launches;
+    BnLaunch b = S.bn;
+    b.p.num_m_tiles = units * L3.rows_per_unit() / kTcBlockM;
+    if (!h->profiling) return bn_launch(b, h->num_sms, s);
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+        if (!h->ev_pool.empty()) { ev[i] = h->ev_pool.back(); h->ev_pool.pop_back(); }
+        else HMV_CUDA(cudaEventCreate(&ev[i]));
+    }
+    HMV_CUDA(cudaEventRecord(ev[0], s));
+    const int rc = bn_launch(b, h->num_sms, s);
+    HMV_CUDA(cudaEventRecord(ev[1], s));
+    hmv_handle::ProfRec r{S.l3, units, ev[0], ev[1], -1};
+    r.seam = seam;
+    h->prof.push_back(r);
+    return rc;
+}
+
 static Epilogue make_ep(void* out, int ldc, int out_mode, int act) {
     Epilogue e{};
     e.out = out; e.ldc = ldc; e.out_mode = out_mode; e.act = act;
@@ -594,6 +627,30 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
     return 0;
 }
 
+// Fused launch plan for conv3 of one layer3 block + conv1 of the next one (both 1x1, P = 256).
+static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
+    const Layer& A = h->layers[l3];
+    const Layer& B = h->layers[l1];
+    HMV_CHECK(A.kind == LK_FLAT && B.kind == LK_FLAT && A.cin == 256 && A.cout == 1024 && B.cin == 1024 && B.cout == 256 &&
+                  A.rows_per_unit() % kTcBlockM == 0 && A.tc.mode == TC_STORE_RES && B.tc.mode != TC_DIRECT && B.in == A.ep.out,
+              "fused bottleneck seam: unexpected layer plan in " + name);
+    FusedSeam S;
+    S.name = name; S.l3 = l3; S.l1 = l1;
+    BnLaunch& b = S.bn;
+    memset(&b.p, 0, sizeof(b.p));
+    const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
+    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, 128) ||
+        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, 256)) {
+        set_error(std::string(get_error()) + " [fused-seam maps of " + name + "]");
+        return 1;
+    }
+    b.tmRes = A.tc.tmR; b.tmOut = A.tc.tmC; b.tmY1 = B.tc.tmC;
+    b.p.bias3 = A.bias; b.p.bias1 = B.bias;
+    b.p.err_flag = h->err_flag_dev;
+    h->seams.push_back(S);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan: buffers, layers, descriptors (hmv_prepare)
 // ------------------------------------------------------------------------------------------------
@@ -665,7 +722,15 @@ static int build_backbone(hmv_handle* h) {
             const bool ds = b == 0 && (st != 1 || C != pl * 4);
             int idx;
             if (add_conv(h, sp + ".conv1", p + ".conv1", p + ".bn1", false, C, pl, 1, 1, H, W, cur, h->bufT1, ACT_RELU, nullptr, &idx)) return 1;
-            add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W);
+            if (h->bf16 && h->fuse_next && li == 2 && b >= 1 && !h->backbone.empty() && h->backbone.back().kind == SK_GEMM) {
+                // the previous block's conv3 step also produces this conv1 (bottleneck_next_tc.cu): no step of its own
+                Step& prev = h->backbone.back();
+                if (add_seam(h, prev.name, prev.layer, idx)) return 1;
+                prev.kind = SK_SEAM;
+                prev.layer = static_cast<int>(h->seams.size()) - 1;
+            } else {
+                add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W);
+            }
             int idx2;
             if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx2)) return 1;
             const bool fuse = h->bf16 && ((h->fuse_mask >> li) & 1);
@@ -897,6 +962,8 @@ static int run_backbone_t(hmv_handle* h, const float* x, int n_img, int num_step
                                  h->num_sms, h->err_flag_dev, s)) return 1;
         } else if (st.kind == SK_TAIL) {
             if (run_tail(h, st.layer, n_img, s)) return 1;
+        } else if (st.kind == SK_SEAM) {
+            if (run_seam(h, st.layer, n_img, s)) return 1;
         } else if (st.kind == SK_MAXPOOL) {
             ++h->launches;
             if (maxpool_launch<T>(static_cast<const T*>(st.in), static_cast<T*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s)) return 1;
@@ -1073,7 +1140,11 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
         return 1;
     }
     *h->err_flag_host = 0;
-    if (h->bf16 && (hmv::tc_init() || hmv::bt_init())) { delete h; return 1; }
+    if (h->bf16 && (hmv::tc_init() || hmv::bt_init() || hmv::bn_init())) { delete h; return 1; }
+    {
+        const char* e = getenv("HMV_FUSE_NEXT");
+        h->fuse_next = e && e[0] == '1';
+    }
     {
         const char* u = getenv("HMV_FUSION_UNFUSED");
         h->fuse_block = !(u && u[0] == '1');
@@ -1688,6 +1759,11 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         std::string name = L.name;
         int ncol = L.cout;
         double kcol = kreal;
+        if (r.seam >= 0) {                            // fused conv3(b) + conv1(b+1)
+            const hmv::Layer& L1 = h->layers[h->seams[r.seam].l1];
+            flop += 2.0 * M * L1.cout * L1.cin;
+            name = L.name + "+next.conv1";
+        }
         if (r.tail >= 0) {                            // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3
             const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
             flop += 2.0 * M * L3.cout * L3.cin;
