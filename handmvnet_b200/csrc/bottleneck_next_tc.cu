@@ -16,8 +16,10 @@
 //   residual was prefetched into (128B swizzle = the canonical K-major A operand layout) -> TMA store of the block output
 //   + "A ready" to the MMA issuer;  E1 = acc1 -> +bias1 -> ReLU -> bf16 -> TMA store of the next block's conv1 output.
 //   A slot is recycled when the TMA store has read it AND the T1 MMAs that use it have retired.
-//   TMEM: acc1 at columns [0, 256), acc3 double-buffered at 256 / 384.   Shared memory: 4 operand stages of 32 KiB
-//   and 6 chunk slots of 16 KiB.
+//   TMEM: acc1 at columns [0, 256), acc3 double-buffered at 256 / 384.   Shared memory: 5 operand stages of 32 KiB
+//   and 4 chunk slots of 16 KiB (measured: ring depth matters more than slot slack - 4 stages + 6 slots 0.457 ms,
+//   3 stages + 8 slots with a two-chunk lag 0.50 ms, 5 stages + 4 slots 0.40 ms per B=64 launch; the two separate
+//   kernels take 0.269 + 0.166 ms).
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -32,9 +34,10 @@ constexpr int kBnNch = kBnN3 / kBnChunk;                        // 8 chunks per 
 constexpr int kBnKb3 = kBnP / kTcBlockK;                        // 4 K blocks per T3
 constexpr int kBnSlotCols = 64;
 constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
-constexpr int kBnSlots = 6;
+constexpr int kBnSlots = 4;
 constexpr int kBnStageBytes = 32 * 1024;                        // T3: A 16 KiB + W3 chunk 16 KiB; T1: W1 K block 32 KiB
-constexpr int kBnStages = 4;
+constexpr int kBnStages = 5;
+constexpr int kBnLag = 1;                                        // T1(c - kBnLag) follows T3(c): the epilogue of chunk c-2 is long done by then
 constexpr int kBnSlotsPerTile = 2 * kBnNch + kBnP / kBnSlotCols; // 16 conv3 slots + 4 conv1 slots
 constexpr int kBnSmemBytes = kBnStages * kBnStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
 static_assert(kBnSmemBytes <= 227 * 1024, "shared memory budget");
@@ -43,9 +46,11 @@ template <typename F3, typename F1>
 __device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
     for (int c = 0; c < kBnNch; ++c) {
         if (!t3(c)) return false;
-        if (c >= 1 && !t1(c - 1)) return false;
+        if (c >= kBnLag && !t1(c - kBnLag)) return false;
     }
-    return t1(kBnNch - 1);
+    for (int c = kBnNch - kBnLag; c < kBnNch; ++c)
+        if (!t1(c)) return false;
+    return true;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)

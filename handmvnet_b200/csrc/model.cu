@@ -148,7 +148,7 @@ struct hmv_handle {
     std::vector<Step> backbone;
     std::vector<FusedTail> tails;
     std::vector<FusedSeam> seams;
-    bool fuse_next = false;                       // HMV_FUSE_NEXT=1: layer3 conv3(b) + conv1(b+1) in one kernel
+    bool fuse_next = true;                        // HMV_FUSE_NEXT=0: layer3 conv3(b) and conv1(b+1) as separate kernels
     int fuse_mask = 3;                            // bottleneck widths whose conv2+conv3 run fused: bit0 P=64, bit1 P=128, bit2 P=256 (HMV_FUSE_TAIL=<mask>)
     std::vector<FusionLayerPlan> fusion;
     int pose0 = -1, pose3 = -1, samp = -1;
@@ -1143,7 +1143,7 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     if (h->bf16 && (hmv::tc_init() || hmv::bt_init() || hmv::bn_init())) { delete h; return 1; }
     {
         const char* e = getenv("HMV_FUSE_NEXT");
-        h->fuse_next = e && e[0] == '1';
+        h->fuse_next = !(e && e[0] == '0');
     }
     {
         const char* u = getenv("HMV_FUSION_UNFUSED");
