@@ -53,12 +53,17 @@ __device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
     return true;
 }
 
+// CL = 2 (opt-in, HMV_SEAM_CLUSTER=1): clusters of two CTAs on neighbouring M tiles; every weight tile (W3 chunk K block,
+// W1 K block) is loaded half by each CTA and multicast into both, so the weights cross L2 -> SM once per pair (the
+// timing model in tools/seam_timing_model.py puts the kernel on the SM's TMA fill bandwidth).  tmW3 / tmW1 then carry
+// half-height boxes; an operand stage is refilled only after BOTH CTAs consumed it (`empty` count 2, multicast commit).
+template <int CL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 output [rows, 256], load box {64, 128}
-                       const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}
+                       const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}  (CL = 2: {64, 64})
                        const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 1024], load box {64, 128}
                        const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 32}
-                       const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}
+                       const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}  (CL = 2: {64, 128})
                        const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
                        const __grid_constant__ BnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -80,12 +85,13 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY2); prefetch_tmap(&tmW3); prefetch_tmap(&tmRes); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmY1);
         for (int i = 0; i < kBnStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, CL);                  // one commit per CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(t3full0 + 8 * i, 1);
@@ -107,13 +113,19 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer's barriers exist before anything remote lands on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
     pdl_launch_dependents();
 
-    const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+    // CL == 1: this CTA's tiles are blockIdx.x, + gridDim.x, ...   CL == 2: the cluster walks pairs of M tiles and this
+    // CTA takes tile 2 * pair + rank; a tile past the end is a dummy (zero-filled loads, clipped stores).
+    const int units = CL == 2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    const int first = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int step = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int n_i = (units - first + step - 1) / step;
+    auto tile_of = [&](int i) { return CL == 2 ? 2 * (first + i * step) + static_cast<int>(crank) : first + i * step; };
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring (same order as the MMA issuer consumes it) =====================
@@ -130,7 +142,11 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             const uint32_t sa = smem_base + stage * kBnStageBytes;
                             mbar_arrive_expect_tx(fb, kBnStageBytes);
                             tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
-                            tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            if (CL == 2)
+                                tma_load_2d_mc(sa + kBnStageBytes / 2 + crank * (kBnStageBytes / 4), &tmW3, fb, kb * kTcBlockK,
+                                               c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2), static_cast<uint16_t>(3));
+                            else
+                                tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -140,7 +156,11 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52)) return false;
                             const uint32_t fb = full0 + 8 * stage;
                             mbar_arrive_expect_tx(fb, kBnStageBytes);
-                            tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            if (CL == 2)
+                                tma_load_2d_mc(smem_base + stage * kBnStageBytes + crank * (kBnStageBytes / 2), &tmW1, fb,
+                                               (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2), static_cast<uint16_t>(3));
+                            else
+                                tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -174,7 +194,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
                                 umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
                                          (kb | k) != 0 ? 1u : 0u);
-                            umma_commit(empty0 + 8 * stage);
+                            if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));
+                            else umma_commit(empty0 + 8 * stage);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         umma_commit(t3full0 + 8 * s);
@@ -196,7 +217,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
                                 umma_f16(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
                                          (c | j | k) != 0 ? 1u : 0u);
-                            umma_commit(empty0 + 8 * stage);
+                            if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));
+                            else umma_commit(empty0 + 8 * stage);
                             umma_commit(sfree0 + 8 * slot);                                // the slot's MMAs have retired
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
@@ -317,6 +339,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer may still multicast into this CTA / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -326,14 +349,35 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 }  // namespace
 
 int bn_init() {
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
     return 0;
 }
 
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0) return 0;
+    if (l.cluster == 2) {              // tmW3 / tmW1 carry half-height boxes
+        static int max_clusters = -1;
+        if (max_clusters < 0) {        // the persistent grid must be co-resident; clusters are placed inside one GPC
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = kBnSmemBytes;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int n = 0;
+            HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, bottleneck_next_kernel<2>, &qc));
+            HMV_CHECK(n > 0, "no 2-CTA cluster of the seam kernel fits on this device");
+            max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+        }
+        const int pairs = (l.p.num_m_tiles + 1) / 2;
+        const int clusters = pairs < max_clusters ? pairs : max_clusters;
+        HMV_CUDA(launch_kernel_cluster(bottleneck_next_kernel<2>, dim3(2 * clusters), dim3(kTcThreads), 2, kBnSmemBytes, stream, l.tmY2,
+                                       l.tmW3, l.tmRes, l.tmOut, l.tmW1, l.tmY1, l.p));
+        return 0;
+    }
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
-    HMV_CUDA(launch_kernel(bottleneck_next_kernel, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
+    HMV_CUDA(launch_kernel(bottleneck_next_kernel<1>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
                            l.tmW1, l.tmY1, l.p));
     return 0;
 }

@@ -94,6 +94,7 @@ struct BnParams {
 struct BnLaunch {
     CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;
     BnParams p;
+    int cluster;                       // 1, or 2: CTA pairs with multicast weight tiles (tmW3 / tmW1 are half-height boxes)
 };
 int bn_init();
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream);

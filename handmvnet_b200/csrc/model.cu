@@ -639,8 +639,10 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
     BnLaunch& b = S.bn;
     memset(&b.p, 0, sizeof(b.p));
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
-    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, 128) ||
-        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, 256)) {
+    static const bool seam_cluster = [] { const char* e = getenv("HMV_SEAM_CLUSTER"); return e && e[0] == '1'; }();   // opt-in
+    b.cluster = seam_cluster ? 2 : 1;
+    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, seam_cluster ? 64 : 128) ||
+        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, seam_cluster ? 128 : 256)) {
         set_error(std::string(get_error()) + " [fused-seam maps of " + name + "]");
         return 1;
     }
