@@ -11,6 +11,10 @@ Calibration (B=64, 2560 tiles on 148 SMs = 17.3 tiles per CTA, 1.6 GHz): measure
 (3, 8, 2) / (4, 6, 1) / (5, 4, 1) = 46k / 42k / 37k cycles per tile.
 
     python tools/seam_timing_model.py
+
+Outcome (kept as a record): the fit needs a per-SM TMA fill port of ~48 B/clk and then predicts -20 % from multicasting the
+weight tiles over a 2-CTA cluster; the variant was built (HMV_SEAM_CLUSTER=1) and measured -1 %, i.e. the fill-bandwidth
+hypothesis is wrong and the kernel is bound by a latency chain the model does not capture.
 """
 import heapq
 import itertools
