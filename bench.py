@@ -7,11 +7,17 @@ Own arm.  A "step" is one forward of the release HO3D configuration (5 views, 25
 backbone -> cross-attention fusion -> Chebyshev GCN head) over a synthetic batch of B=64 samples per GPU
 (BASELINE.json configs[1]; weak scaling: every rank gets its own 64 samples, no data-path collective, only an
 NCCL all-gather of the [B,21,3] poses).  `value` = samples all ranks processed / max-over-ranks device time with
-the inputs resident in HBM; `e2e` = the same through `HandMvNet.forward_host` (hmv_forward_host) with pinned
-HOST buffers, host->device copies of the step's inputs and device->host copies of the poses inside the timed
-region.  `roofline` describes the dominant kernel (the tcgen05 implicit-GEMM conv), timed per launch with CUDA
-events on its stream in a second pass over the same steps; `cpu_baseline` is the CPU oracle (a port of the
-reference's torch forward) timed on this box's host cores on a bounded sample.
+the inputs resident in HBM; `e2e` = the same through `HandMvNet.forward_host_async` (hmv_forward_host_u8_async) with
+pinned HOST buffers holding the uint8 image crops the reference's data pipeline produces in front of ToTensor +
+Normalize (datasets/ho3d.py:35-40), host->device copies of the step's inputs and device->host copies of the poses
+inside the timed region (`e2e.fp32_input` = the same loop fed host-normalised fp32 tensors, 4x the bytes).
+`roofline` describes the dominant kernel class of the step (by device time), timed per launch with CUDA events on its
+stream in a second pass over the same steps, against the roofline that bounds it; `roofline.classes` lists every
+tcgen05 kernel class the same way and `roofline.all_tc` their aggregate.  `gpu_eager_baseline` (N = 1) is the oracle's
+full forward run as eager PyTorch on the same GPU (cudnn.benchmark, fp32 with TF32 convolutions and bf16 autocast) -
+the north star's "x the reference's eager forward at B=64"; `latency_b1` is the p50 / p99 of one B=1 forward
+(reference protocol src/eval_fps.py:68-106) for the 5- and 8-view configurations; `cpu_baseline` is the CPU oracle (a
+port of the reference's torch forward) timed on this box's host cores on the same bounded sample the reference arm uses.
 
 Reference arm (`--impl reference`): the reference's algorithm on the host CPU cores (oracle port, all threads),
 same metric / config, each step a bounded sample of the workload.
@@ -123,11 +129,14 @@ def cpu_oracle_throughput(batch, iters, warmup, views=5):
     return batch * len(times) / total, total / len(times) * 1e3, torch.get_num_threads()
 
 
+CPU_SAMPLE_B = 2       # samples per CPU step: the ONE bounded sample both `--impl reference` and `cpu_baseline` time
+
+
 def run_reference(args, lines):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 2
+    sample_b = CPU_SAMPLE_B
     ps, ms, cores = cpu_oracle_throughput(sample_b, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": ps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -227,73 +236,69 @@ def run_own(args, lines):
     assert torch.isfinite(out["joints_cam"]).all()
 
     # ---- end to end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region) ----
-    h2d = x.numel() * 4 + bbox_host.numel() * 4 + intr_host.numel() * 4
-    d2h = B * 21 * 3 * 4 + B * views * 21 * 2 * 4
-    e2e_s = float("nan")
-    if not args.no_e2e:
-        cam_host = {"intrinsic": intr_host}
-        for _ in range(max(1, args.warmup // 2)):
-            model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+    # Streaming loop of a caller that feeds batch after batch (eval_fps.py:79-92): step k+1 is enqueued before the
+    # results of step k are awaited, so its host->device copy overlaps step k's compute.  Every step still copies its
+    # own inputs from pinned host memory and reads its poses back, all inside the timed region.
+    def host_loop(x_h):
+        for _ in range(2):
+            model.forward_host_async(x_h, bbox_host, cam_host, want_heatmap=False).result(recycle=True)
         barrier()
-        # streaming loop of a caller that feeds batch after batch (eval_fps.py:79-92): step k+1 is enqueued before the
-        # results of step k are awaited, so its host->device copy overlaps step k's compute.  Every step still copies
-        # its own 251 MB of inputs from pinned host memory and reads its poses back, all inside the timed region.
         t0 = time.perf_counter()
-        prev = None
+        prev, ho = None, None
         for _ in range(args.steps):
-            tk = model.forward_host_async(x_host, bbox_host, cam_host, want_heatmap=False)
+            tk = model.forward_host_async(x_h, bbox_host, cam_host, want_heatmap=False)
             if prev is not None:
                 ho = prev.result(recycle=True)
             prev = tk
         ho = prev.result(recycle=True)
         torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
+        dt = time.perf_counter() - t0
         barrier()
         assert torch.isfinite(ho["joints_cam"]).all()
-        d2h = ho["joints_cam"].numel() * 4 + ho["joints_crop_img"].numel() * 4
+        return dt, ho["joints_cam"].numel() * 4 + ho["joints_crop_img"].numel() * 4
+
+    small = bbox_host.numel() * 4 + intr_host.numel() * 4
+    e2e_u8_s = e2e_f32_s = float("nan")
+    d2h = B * 21 * 3 * 4 + B * views * 21 * 2 * 4
+    if not args.no_e2e:
+        cam_host = {"intrinsic": intr_host}
+        # headline: uint8 crops, what the reference's data pipeline holds in front of ToTensor + Normalize
+        xu_host = torch.randint(0, 256, (B, views, 3, 256, 256), generator=g, dtype=torch.uint8).pin_memory()
+        e2e_u8_s, d2h = host_loop(xu_host)
+        # the same loop fed host-normalised fp32 tensors (4x the bytes: host-memory bound when 8 ranks share one socket)
+        e2e_f32_s, _ = host_loop(x_host)
         # latency form of the same call (one batch at a time, wait before the next)
         t0 = time.perf_counter()
         for _ in range(max(3, args.steps // 4)):
-            model.forward_host(x_host, bbox_host, cam_host, want_heatmap=False)
+            model.forward_host(xu_host, bbox_host, cam_host, want_heatmap=False)
         e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / max(3, args.steps // 4)
-        # the same streaming loop fed with uint8 images (ToTensor + Normalize fused into the stem kernel): 4x less H2D
-        xu_host = torch.randint(0, 256, (B, views, 3, 256, 256), generator=g, dtype=torch.uint8).pin_memory()
-        for _ in range(2):
-            model.forward_host_async(xu_host, bbox_host, cam_host, want_heatmap=False).result(recycle=True)
-        barrier()
-        t0 = time.perf_counter()
-        prev = None
-        for _ in range(args.steps):
-            tk = model.forward_host_async(xu_host, bbox_host, cam_host, want_heatmap=False)
-            if prev is not None:
-                prev.result(recycle=True)
-            prev = tk
-        prev.result(recycle=True)
-        torch.cuda.synchronize(dev)
-        e2e_u8_s = time.perf_counter() - t0
-        barrier()
 
-    # ---- per-launch timing of the dominant kernel: same steps again with CUDA events around every launch ----
+    # ---- per-launch timing of the tcgen05 kernels: same steps again with CUDA events around every launch ----
     model.profile(True)
     for _ in range(args.steps):
         model(x, bbox, cam)
-    csv = os.path.join(ROOT, "gpurun_out", "tc_launches.csv") if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
-    tc_ms, tc_flops, tc_n = model.profile_read(csv)
+    import tempfile
+    csv_path = os.path.join(tempfile.gettempdir(), f"hmv_tc_launches_{os.getpid()}.csv")
+    tc_ms, tc_flops, tc_n = model.profile_read(csv_path)
     phases = {k: v / args.steps for k, v in model.profile_phases().items()}
     model.profile(False)
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 and not args.no_clocks else None
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        import shutil
+        shutil.copyfile(csv_path, os.path.join(ROOT, "gpurun_out", "tc_launches.csv"))
 
-    times = torch.tensor([dev_ms, 0.0 if args.no_e2e else e2e_s * 1e3, 0.0 if args.no_e2e else e2e_u8_s * 1e3], device=dev, dtype=torch.float64)
+    times = torch.tensor([dev_ms, 0.0 if args.no_e2e else e2e_u8_s * 1e3, 0.0 if args.no_e2e else e2e_f32_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_u8_ms = float(times[0]), float(times[1]), float(times[2])
+    dev_ms, e2e_u8_ms, e2e_f32_ms = float(times[0]), float(times[1]), float(times[2])
+    line = None
     if rank == 0:
         peaks = load_peaks()
         value = B * world * args.steps / (dev_ms * 1e-3)
-        achieved = tc_flops / (tc_ms * 1e-3) * 1e-12 if tc_ms > 0 else 0.0
+        step_ms_mean = dev_ms / args.steps
         line = {
             "metric": METRIC if views == 5 else METRIC_FMT.format(v=views), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps,
+            "ms_per_step": step_ms_mean,
             "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -303,46 +308,196 @@ def run_own(args, lines):
                        "l2": f"inputs {x.numel() * 4 / 2**20:.0f} MiB + {0.445 * B:.1f} GB of activations per step exceed the 126 MB L2"},
             "clocks": clocks,
             "e2e": None if args.no_e2e else {
-                "value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                "sync_call_ms": e2e_sync_ms,
-                "uint8_input": {"value": B * world * args.steps / (e2e_u8_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8_ms / args.steps,
-                                "h2d_bytes_per_step": x.numel() + bbox_host.numel() * 4 + intr_host.numel() * 4,
-                                "note": "same loop with uint8 [B,V,3,256,256] images; ToTensor + Normalize (datasets/ho3d.py:35-40) run in the stem kernel"},
-                "api": "HandMvNet.forward_host_async -> hmv_forward_host_async / hmv_host_wait (pinned host buffers, poses copied "
-                       "back; at most 2 steps in flight); sync_call_ms = blocking HandMvNet.forward_host per call"},
+                "value": B * world * args.steps / (e2e_u8_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": xu_host.numel() + small, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_u8_ms / args.steps,
+                "sync_call_ms": e2e_sync_ms, "input": "uint8 [B,V,3,256,256] image crops in pinned host memory",
+                "fp32_input": {"value": B * world * args.steps / (e2e_f32_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_f32_ms / args.steps,
+                               "h2d_bytes_per_step": x.numel() * 4 + small,
+                               "note": "same loop fed host-normalised fp32 [B,V,3,256,256] tensors (the reference module's own input type)"},
+                "api": "HandMvNet.forward_host_async -> hmv_forward_host_u8_async / hmv_host_wait (pinned host buffers; ToTensor + Normalize of "
+                       "datasets/ho3d.py:35-40 run inside the stem kernel; poses copied back; at most 2 steps in flight); "
+                       "sync_call_ms = blocking HandMvNet.forward_host per call"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv_gemm_tc_kernel + bottleneck_tail_kernel (tcgen05 implicit-GEMM convs / linears, fused conv2+conv3 tails)",
-                         "bound": "tensor",
-                         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], **tc_traffic(views, B, args.micro_batch),
-                         "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
-                         "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps,
-                         "kernel_share_of_step": (tc_ms / args.steps) / (dev_ms / args.steps),
-                         "timing": "second pass over the same steps with CUDA events around every launch",
-                         "end_to_end_model_tflops": FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9) * value / world * 1e-12,
-                         "phase_ms_per_step": phases},
+            "roofline": roofline_report(csv_path, args.steps, step_ms_mean, peaks, views, B, args.micro_batch, tc_ms, tc_flops, tc_n,
+                                        FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9) * value / world * 1e-12, phases),
         }
         if world == 1 and not args.no_cpu_baseline:
-            ps, ms, cores = cpu_oracle_throughput(1, 12, 3)
+            ps, ms, cores = cpu_oracle_throughput(CPU_SAMPLE_B, 10, 3)
             line["cpu_baseline"] = {"value": ps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "oracle/handmvnet_oracle.py forward, B=1 x 12 steps (+3 warm-up), fp32, all host threads",
+                                    "sample": f"oracle/handmvnet_oracle.py forward, B={CPU_SAMPLE_B} x 10 steps (+3 warm-up), fp32, all host threads "
+                                              "(the same bounded sample `--impl reference` times)",
                                     "ms_per_forward": ms}
+    # the two legs below allocate: release the model's workspace first
+    del model
+    if world == 1 and rank == 0:
+        if not args.no_eager:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, views, B, step_ms_mean)
+        if not args.no_latency:
+            line["latency_b1"] = latency_b1(dev)
+    if rank == 0:
         lines.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def tc_traffic(views, batch, micro_batch):
-    """DRAM bytes (read + write) per launch of the dominant kernel class, from the committed ncu launch list of one
-    B=64 / 5-view step (profiles/r01/tc_traffic.json); null for any other workload."""
-    path = os.path.join(ROOT, "profiles", "r01", "tc_traffic.json")
+def kernel_class(name):
+    """layer3.2.conv2 -> layer3.x.conv2 ; joints_late_fusion.attn_fusion.0.qkv -> fusion.x.qkv"""
+    import re
+    name = re.sub(r"layer(\d)\.\d+\.", r"layer\1.x.", name)
+    name = re.sub(r"joints_late_fusion\.attn_fusion\.\d+\.", "fusion.x.", name)
+    return name
+
+
+def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, tc_ms, tc_flops, tc_n, model_tflops, phases):
+    """Per kernel class (launches of one class share a geometry): CUDA-event time per launch, algorithmic FLOPs and HBM
+    bytes (SURVEY.md §8d / DESIGN.md §4: every input, residual, output element and every weight once), the roofline
+    that bounds the class (the larger of FLOPs / sustained tensor peak and bytes / measured HBM peak) and the achieved
+    fraction of it.  The headline object describes the class with the largest share of the step."""
+    import csv
+    classes = {}
+    with open(csv_path) as f:
+        for row in csv.DictReader(f):
+            c = classes.setdefault(kernel_class(row["layer"]), {"n": 0, "ms": 0.0, "gflop": 0.0, "mbytes": 0.0})
+            c["n"] += 1
+            c["ms"] += float(row["ms"])
+            c["gflop"] += float(row["gflop"])
+            c["mbytes"] += float(row["mbytes"])
+    tpeak, hpeak = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
+    traffic = load_traffic(views, batch, micro_batch)
+    out = []
+    for name, c in classes.items():
+        ms_l = c["ms"] / c["n"]
+        t_tensor = c["gflop"] / c["n"] / tpeak            # GFLOP / (TFLOP/s) = ms
+        t_hbm = c["mbytes"] / c["n"] / hpeak              # MB / (GB/s) = ms
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        rec = {"kernel": name, "launches_per_step": c["n"] / steps, "ms_per_launch": ms_l, "ms_per_step": c["ms"] / steps,
+               "share_of_step": c["ms"] / steps / step_ms, "bound": bound,
+               "achieved": c["gflop"] / c["ms"] if bound == "tensor" else c["mbytes"] / c["ms"],
+               "peak": tpeak if bound == "tensor" else hpeak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+               "frac": max(t_tensor, t_hbm) / ms_l, "tflops": c["gflop"] / c["ms"], "gbs": c["mbytes"] / c["ms"],
+               "algorithmic_mbytes_per_launch": c["mbytes"] / c["n"], "gflop_per_launch": c["gflop"] / c["n"]}
+        out.append(rec)
+    out.sort(key=lambda r: -r["ms_per_step"])
+    top = dict(out[0]) if out else {}
+    tr = (traffic or {}).get("classes", {}).get(top.get("kernel"))
+    if traffic is None:
+        top["traffic"], top["traffic_note"] = None, "no ncu capture committed for this workload"
+    elif tr is None or abs(tr["launches_per_step"] - top["launches_per_step"]) > 1e-6 or traffic["tc_launches_per_step"] != round(tc_n / steps):
+        top["traffic"] = None
+        top["traffic_note"] = (f"stale ncu capture: {traffic['source']} saw {traffic['tc_launches_per_step']} tcgen05 launches per step, "
+                               f"this run timed {tc_n / steps:.0f}")
+    else:
+        top["traffic"] = tr["dram_bytes_per_launch"]
+        top["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
+        top["traffic_over_algorithmic"] = tr["dram_bytes_per_launch"] / (top["algorithmic_mbytes_per_launch"] * 1e6)
+        top["traffic_per_step_bytes_all_tc"] = traffic["tc_dram_bytes_per_step"]
+        top["traffic_source"] = traffic["source"]
+    top["peak_source"] = peaks["source"] + (" (sustained cuBLAS bf16: kernel timed inside a long step)" if top.get("bound") == "tensor"
+                                             else " (device copy bandwidth)")
+    top["timing"] = "second pass over the same steps with CUDA events around every launch"
+    agg = tc_flops / (tc_ms * 1e-3) * 1e-12 if tc_ms > 0 else 0.0
+    top["all_tc"] = {"kernel": "every tcgen05 launch of the step (implicit-GEMM convs / linears, fused tails, fused seams)", "bound": "tensor",
+                     "achieved": agg, "peak": tpeak, "unit": "TFLOP/s", "frac": agg / tpeak, "launches_per_step": tc_n / steps,
+                     "kernel_ms_per_step": tc_ms / steps, "kernel_share_of_step": tc_ms / steps / step_ms,
+                     "sum_of_class_bounds_ms": sum(r["frac"] * r["ms_per_step"] for r in out),
+                     "end_to_end_model_tflops": model_tflops}
+    top["phase_ms_per_step"] = phases
+    top["classes"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
+                       if k in ("kernel", "launches_per_step", "ms_per_launch", "ms_per_step", "bound", "frac", "tflops", "gbs")} for r in out]
+    return top
+
+
+def load_traffic(views, batch, micro_batch):
+    """DRAM bytes per launch per kernel class from the committed ncu launch list of one B=64 / 5-view step
+    (profiles/r02/tc_traffic.json, written by tools/ncu_step_traffic.py); None for any other workload."""
+    path = os.path.join(ROOT, "profiles", "r02", "tc_traffic.json")
     if views != 5 or batch != 64 or micro_batch != 64 or not os.path.exists(path):
-        return {"traffic": None}
+        return None
     with open(path) as f:
-        t = json.load(f)
-    return {"traffic": t["tc_dram_bytes_per_launch_mean"], "traffic_unit": "bytes per launch (mean over the launches of a step)",
-            "traffic_per_step_bytes": t["tc_dram_bytes_per_step"], "traffic_source": t["source"]}
+        return json.load(f)
+
+
+def gpu_eager_baseline(dev, views, B, own_ms):
+    """The reference's forward as eager PyTorch on THIS GPU (north star: ">= 20x the reference's eager PyTorch forward on
+    1 B200 at B=64"): the oracle's full forward (every stage, constants resident on the device) with the protocol of
+    src/eval_fps.py:17,79-94 - cudnn.benchmark on, no_grad, fp32 (cuDNN convolutions use TF32 by default, as in the
+    reference) and bf16 autocast - timed with CUDA events."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import handmvnet_oracle as O
+    torch.cuda.empty_cache()
+    cfg = O.release_config(views, True)
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0, randomize_norm=False).items()}
+    x, bbox, intr = O.make_inputs(B, views, seed=1234)
+    x, bbox, intr = x.to(dev), bbox.to(dev), intr.to(dev)
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+
+    def timed(iters=8, warm=3):
+        for _ in range(warm):
+            O.forward(sd, cfg, x, bbox, intr)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = O.forward(sd, cfg, x, bbox, intr)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        assert torch.isfinite(out["joints_cam"]).all()
+        return e0.elapsed_time(e1) / iters
+
+    ms32 = timed()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ms16 = timed()
+    torch.backends.cudnn.benchmark = prev
+    del sd, x
+    torch.cuda.empty_cache()
+    return {"what": "oracle/handmvnet_oracle.py full forward as eager PyTorch on the same GPU, cudnn.benchmark=True, CUDA-event timed "
+                    "(restates the loop of src/eval_fps.py:79-94 without the MANO post-processing)",
+            "batch": B, "views": views,
+            "fp32_tf32conv": {"ms_per_step": ms32, "value": B / ms32 * 1e3, "unit": UNIT},
+            "bf16_autocast": {"ms_per_step": ms16, "value": B / ms16 * 1e3, "unit": UNIT},
+            "speedup_vs_eager_fp32": ms32 / own_ms, "speedup_vs_eager_bf16": ms16 / own_ms,
+            "target": 20.0}
+
+
+def latency_b1(dev, iters=300, warm=50):
+    """p50 / p99 of ONE B=1 forward on device-resident inputs (BASELINE.json metric; reference protocol
+    src/eval_fps.py:68-106: one sample per call, timed per call), 5-view HO3D and 8-view DexYCB configurations."""
+    import torch
+    from handmvnet_b200 import HandMvNet
+    from handmvnet_b200.config import release_config
+    out = {}
+    for v in (5, 8):
+        cfg = release_config(v, True)
+        torch.manual_seed(0)
+        m = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision="bf16", micro_batch=1)
+        m.to(dev).eval()
+        m.freeze()
+        m.prepare(dev)
+        x = torch.randn(1, v, 3, 256, 256, device=dev)
+        bbox = torch.tensor([220.0, 140.0, 420.0, 340.0], device=dev).expand(1, v, 4).contiguous()
+        cam = {"intrinsic": torch.tensor([600.0, 600.0, 320.0, 240.0], device=dev).expand(1, v, 4).contiguous()}
+        for _ in range(warm):
+            m(x, bbox, cam)
+        torch.cuda.synchronize(dev)
+        n0 = m.launch_count()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o = m(x, bbox, cam)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        assert torch.isfinite(o["joints_cam"]).all()
+        out[f"views{v}"] = {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[int(len(ts) * 0.99)], "min_ms": ts[0], "iters": iters,
+                            "kernels_per_forward": (m.launch_count() - n0) // iters}
+        del m
+        torch.cuda.empty_cache()
+    out["protocol"] = "B=1 per call, device-resident fp32 inputs, CUDA events around each call (CUDA-graph replay inside the library)"
+    return out
 
 
 def main():
@@ -357,6 +512,8 @@ def main():
     ap.add_argument("--views", type=int, default=5, help="camera views per sample (5 = HO3D release config, 8 = DexYCB)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large-batch sweeps)")
     ap.add_argument("--no-clocks", action="store_true", help="do not run the NVML clock sampler")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg (N=1 only)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B=1 latency leg (N=1 only)")
     ap.add_argument("--ramp-seconds", type=float, default=1.5, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -6,14 +6,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libhandmvnet_b200.so")
 
 PRECISION = {"bf16": 0, "fp32": 1}
-STAGE = {"backbone": 0, "pose": 1, "sample": 2, "fusion": 3, "gcn": 4}
+STAGE = {"backbone": 0, "pose": 1, "sample": 2, "fusion": 3, "gcn": 4, "softargmax": 5}
 TENSOR = {"feat": 0, "heatmap": 1, "xy": 2, "tokens": 3, "fused": 4, "joints": 5}
 
 # every symbol include/handmvnet_b200.h declares
 EXPORTS = ["hmv_create", "hmv_destroy", "hmv_set_weight", "hmv_prepare", "hmv_forward", "hmv_forward_host",
            "hmv_forward_host_async", "hmv_host_wait", "hmv_set_input_norm", "hmv_preprocess", "hmv_forward_u8", "hmv_forward_host_u8_async",
            "hmv_synchronize", "hmv_stage_run", "hmv_tensor_get", "hmv_tensor_set", "hmv_debug_backbone",
-           "hmv_debug_num_steps", "hmv_debug_step_name", "hmv_conv_bn_act", "hmv_profile_enable", "hmv_profile_read", "hmv_profile_phases",
+           "hmv_debug_num_steps", "hmv_debug_step_name", "hmv_debug_step_io", "hmv_debug_step_run", "hmv_conv_bn_act", "hmv_profile_enable", "hmv_profile_read", "hmv_profile_phases",
            "hmv_launch_count", "hmv_num_sms",
            "hmv_last_error", "hmv_version"]
 
@@ -58,6 +58,8 @@ def load():
     lib.hmv_debug_num_steps.argtypes = [vp]
     lib.hmv_debug_step_name.argtypes = [vp, i32]
     lib.hmv_debug_step_name.restype = ctypes.c_char_p
+    lib.hmv_debug_step_io.argtypes = [vp, i32, ctypes.c_char_p, i32]
+    lib.hmv_debug_step_run.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     lib.hmv_conv_bn_act.argtypes = [i32, f32p, f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, i32,
                                     ctypes.POINTER(ctypes.c_float), i32, vp]
     lib.hmv_profile_enable.argtypes = [vp, i32]

@@ -23,6 +23,9 @@
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <map>
+#include <utility>
+
 namespace hmv {
 
 namespace {
@@ -357,7 +360,10 @@ int bn_init() {
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0) return 0;
     if (l.cluster == 2) {              // tmW3 / tmW1 carry half-height boxes
-        static int max_clusters = -1;
+        static std::map<std::pair<int, int>, int> cache;                   // per (device, persistent-grid cap)
+        int dev = 0;
+        HMV_CUDA(cudaGetDevice(&dev));
+        int& max_clusters = cache.emplace(std::make_pair(dev, num_sms), -1).first->second;
         if (max_clusters < 0) {        // the persistent grid must be co-resident; clusters are placed inside one GPC
             cudaLaunchConfig_t qc{};
             qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = kBnSmemBytes;

@@ -3,6 +3,9 @@
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <map>
+#include <utility>
+
 namespace hmv {
 
 // ------------------------------------------------------------------------------------------------
@@ -470,7 +473,10 @@ static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     if constexpr (BN == 256) {
         if (l.cluster == 2) {          // pairs of CTAs sharing multicast weight tiles (l.tmB has a BN/2-row box)
             // the persistent grid must be co-resident: clusters are placed inside one GPC, so fewer than num_sms / 2 may fit
-            static int max_clusters = -1;
+            static std::map<std::pair<int, int>, int> cache;               // per (device, persistent-grid cap)
+            int dev = 0;
+            HMV_CUDA(cudaGetDevice(&dev));
+            int& max_clusters = cache.emplace(std::make_pair(dev, num_sms), -1).first->second;
             if (max_clusters < 0) {
                 cudaLaunchConfig_t qc{};
                 qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = TcCfg<BN, MODE>::kSmemBytes;

@@ -94,6 +94,11 @@ struct HostTensor {
 };
 
 enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4, SK_SEAM = 5 };
+struct StepIO {                                    // one activation tensor a backbone step reads / writes (NHWC in the workspace)
+    void* ptr;
+    std::string tap;                              // name of the oracle tap holding the same tensor (oracle.backbone(per_layer=True))
+    int C, H, W;
+};
 struct Step {
     int kind;
     std::string name;
@@ -101,6 +106,7 @@ struct Step {
     const void* in = nullptr;
     void* out = nullptr;
     int C = 0, H = 0, W = 0;                      // output geometry (NHWC)
+    std::vector<StepIO> ins, outs;                // teacher-forced single-step runs (hmv_debug_step_run)
 };
 
 // conv2 + conv3 (+residual) of one bottleneck as a single launch (bottleneck_tc.cu)
@@ -149,6 +155,7 @@ struct hmv_handle {
     std::vector<FusedTail> tails;
     std::vector<FusedSeam> seams;
     bool fuse_next = true;                        // HMV_FUSE_NEXT=0: layer3 conv3(b) and conv1(b+1) as separate kernels
+    bool seam_cluster = false;                    // HMV_SEAM_CLUSTER=1: the seam kernel as 2-CTA clusters with multicast weights
     int fuse_mask = 3;                            // bottleneck widths whose conv2+conv3 run fused: bit0 P=64, bit1 P=128, bit2 P=256 (HMV_FUSE_TAIL=<mask>)
     std::vector<FusionLayerPlan> fusion;
     int pose0 = -1, pose3 = -1, samp = -1;
@@ -207,6 +214,11 @@ struct hmv_handle {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase id, event) recorded while profiling
+    // The entry points share ONE workspace but may be called on different streams (the caller's, graph_stream,
+    // compute_stream): every entry point first makes its stream wait for the last work that touched the workspace.
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_valid = false;
 };
 
 namespace hmv {
@@ -220,6 +232,31 @@ static int dev_alloc(hmv_handle* h, void** p, size_t bytes, bool zero = true) {
 template <typename P>
 static int dev_alloc_t(hmv_handle* h, P** p, size_t bytes, bool zero = true) {
     return dev_alloc(h, reinterpret_cast<void**>(p), bytes, zero);
+}
+
+// Switches to the handle's device for the duration of a C entry point and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int dev) : want(dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// workspace ordering across streams (see hmv_handle::ws_event)
+static int ws_acquire(hmv_handle* h, cudaStream_t s) {
+    if (h->ws_valid && h->ws_stream != s) HMV_CUDA(cudaStreamWaitEvent(s, h->ws_event, 0));
+    return 0;
+}
+static int ws_release(hmv_handle* h, cudaStream_t s) {
+    if (!h->ws_event) HMV_CUDA(cudaEventCreateWithFlags(&h->ws_event, cudaEventDisableTiming));
+    HMV_CUDA(cudaEventRecord(h->ws_event, s));
+    h->ws_stream = s;
+    h->ws_valid = true;
+    return 0;
 }
 
 static int upload_f32(hmv_handle* h, float** dst, const std::vector<float>& v) {
@@ -589,9 +626,12 @@ static int add_linear(hmv_handle* h, const std::string& name, const std::vector<
     return 0;
 }
 
-static int add_gemm_step(hmv_handle* h, const std::string& name, int layer, void* out, int C, int H, int W) {
+static int add_gemm_step(hmv_handle* h, const std::string& name, int layer, void* out, int C, int H, int W,
+                         std::vector<StepIO> ins = {}) {
     Step st;
     st.kind = SK_GEMM; st.name = name; st.layer = layer; st.out = out; st.C = C; st.H = H; st.W = W;
+    st.ins = std::move(ins);
+    st.outs.push_back({out, name, C, H, W});
     h->backbone.push_back(st);
     return 0;
 }
@@ -639,7 +679,7 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
     BnLaunch& b = S.bn;
     memset(&b.p, 0, sizeof(b.p));
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
-    static const bool seam_cluster = [] { const char* e = getenv("HMV_SEAM_CLUSTER"); return e && e[0] == '1'; }();   // opt-in
+    const bool seam_cluster = h->seam_cluster;        // opt-in (HMV_SEAM_CLUSTER=1)
     b.cluster = seam_cluster ? 2 : 1;
     if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, seam_cluster ? 64 : 128) ||
         tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, seam_cluster ? 128 : 256)) {
@@ -708,6 +748,8 @@ static int build_backbone(hmv_handle* h) {
     }
     Step mp; mp.kind = SK_MAXPOOL; mp.name = "maxpool"; mp.in = h->bufT1; mp.out = h->bufX; mp.C = 64;
     mp.H = h->img / 4; mp.W = h->img / 4;
+    mp.ins.push_back({h->bufT1, "conv1", 64, h->img / 2, h->img / 2});
+    mp.outs.push_back({h->bufX, "maxpool", 64, mp.H, mp.W});
     h->backbone.push_back(mp);
     }
 
@@ -715,6 +757,7 @@ static int build_backbone(hmv_handle* h) {
     void* cur = h->bufX;
     void* nxt = h->bufY;
     int C = 64, H = h->img / 4, W = h->img / 4;
+    std::string cur_name = "maxpool";                 // oracle tap of the tensor in `cur`
     const int blocks[3] = {3, 4, 6}, planes[3] = {64, 128, 256}, strides[3] = {1, 2, 1};
     for (int li = 0; li < 3; ++li) {
         for (int b = 0; b < blocks[li]; ++b) {
@@ -730,30 +773,37 @@ static int build_backbone(hmv_handle* h) {
                 if (add_seam(h, prev.name, prev.layer, idx)) return 1;
                 prev.kind = SK_SEAM;
                 prev.layer = static_cast<int>(h->seams.size()) - 1;
+                prev.outs.push_back({h->bufT1, sp + ".conv1", pl, H, W});
             } else {
-                add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W);
+                add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W, {{cur, cur_name, C, H, W}});
             }
             int idx2;
             if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx2)) return 1;
             const bool fuse = h->bf16 && ((h->fuse_mask >> li) & 1);
-            if (!fuse) add_gemm_step(h, sp + ".conv2", idx2, h->bufT2, pl, H / st, W / st);
+            if (!fuse) add_gemm_step(h, sp + ".conv2", idx2, h->bufT2, pl, H / st, W / st, {{h->bufT1, sp + ".conv1", pl, H, W}});
             const void* res = cur;
+            StepIO res_io{cur, cur_name, C, H, W};
             if (ds) {
                 if (add_conv(h, sp + ".downsample", p + ".downsample.0", p + ".downsample.1", false, C, pl * 4, 1, st, H, W, cur, h->bufDS, ACT_NONE, nullptr, &idx)) return 1;
-                add_gemm_step(h, sp + ".downsample", idx, h->bufDS, pl * 4, H / st, W / st);
+                add_gemm_step(h, sp + ".downsample", idx, h->bufDS, pl * 4, H / st, W / st, {{cur, cur_name, C, H, W}});
                 res = h->bufDS;
+                res_io = StepIO{h->bufDS, sp + ".downsample", pl * 4, H / st, W / st};
             }
             if (add_conv(h, sp + ".conv3", p + ".conv3", p + ".bn3", false, pl, pl * 4, 1, 1, H / st, W / st, h->bufT2, nxt, ACT_RELU, res, &idx)) return 1;
             if (fuse) {
                 if (add_tail(h, sp + ".conv3", idx2, idx)) return 1;
                 Step ts; ts.kind = SK_TAIL; ts.name = sp + ".conv3"; ts.layer = static_cast<int>(h->tails.size()) - 1;
                 ts.out = nxt; ts.C = pl * 4; ts.H = H / st; ts.W = W / st;
+                ts.ins.push_back({h->bufT1, sp + ".conv1", pl, H, W});
+                ts.ins.push_back(res_io);
+                ts.outs.push_back({nxt, sp + ".conv3", pl * 4, H / st, W / st});
                 h->backbone.push_back(ts);
             } else {
-                add_gemm_step(h, sp + ".conv3", idx, nxt, pl * 4, H / st, W / st);
+                add_gemm_step(h, sp + ".conv3", idx, nxt, pl * 4, H / st, W / st, {{h->bufT2, sp + ".conv2", pl, H / st, W / st}, res_io});
             }
             void* t = cur; cur = nxt; nxt = t;
             C = pl * 4; H /= st; W /= st;
+            cur_name = sp + ".conv3";
         }
     }
     h->featbuf = cur;
@@ -1116,7 +1166,8 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     int ndev = 0;
     HMV_CUDA(cudaGetDeviceCount(&ndev));
     HMV_CHECK(ndev > 0, "no CUDA device: handmvnet_b200 has no CPU fallback");
-    HMV_CUDA(cudaSetDevice(cfg->device));
+    HMV_CHECK(cfg->device >= 0 && cfg->device < ndev, "hmv_create: no such CUDA device");
+    hmv::DeviceGuard guard(cfg->device);
     cudaDeviceProp prop;
     HMV_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     HMV_CHECK(prop.major == 10, "handmvnet_b200 is built for sm_100a (Blackwell B200) only");
@@ -1146,6 +1197,8 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     {
         const char* e = getenv("HMV_FUSE_NEXT");
         h->fuse_next = !(e && e[0] == '0');
+        const char* c = getenv("HMV_SEAM_CLUSTER");
+        h->seam_cluster = c && c[0] == '1';
     }
     {
         const char* u = getenv("HMV_FUSION_UNFUSED");
@@ -1159,8 +1212,9 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
 
 int hmv_destroy(hmv_handle* h) {
     if (!h) return 0;
-    cudaSetDevice(h->cfg.device);
+    hmv::DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
+    if (h->ws_event) cudaEventDestroy(h->ws_event);
     for (void* p : h->allocs) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         if (h->xstage[i]) cudaFree(h->xstage[i]);
@@ -1201,7 +1255,7 @@ int hmv_set_weight(hmv_handle* h, const char* name, const float* data, const int
 int hmv_prepare(hmv_handle* h) {
     HMV_CHECK(h, "hmv_prepare: null handle");
     HMV_CHECK(!h->prepared, "hmv_prepare called twice");
-    HMV_CUDA(cudaSetDevice(h->cfg.device));
+    hmv::DeviceGuard guard(h->cfg.device);
     if (hmv::build_backbone(h)) return 1;
     if (hmv::build_heads(h)) return 1;
     {   // small-batch CUDA-graph path (HMV_NO_GRAPH=1 disables it)
@@ -1356,16 +1410,21 @@ int hmv_forward(hmv_handle* h, const float* x, const float* bbox, const float* i
     HMV_CHECK(x || batch == 0, "hmv_forward: x is null");
     HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
     if (hmv::check_flag(h)) return 1;
+    if (batch == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (batch > 0 && batch <= h->graph_max_batch && !h->profiling) return forward_graph(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
-    if (batch > 0 && h->graph_max_batch > 0 && h->ptr_graphs_ok && !h->profiling)
-        return forward_graph_ptr(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
-    return forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    if (hmv::ws_acquire(h, s)) return 1;
+    int rc;
+    if (batch <= h->graph_max_batch && !h->profiling) rc = forward_graph(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    else if (h->graph_max_batch > 0 && h->ptr_graphs_ok && !h->profiling)
+        rc = forward_graph_ptr(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    else rc = forward_eager(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
+    if (rc) return rc;
+    return hmv::ws_release(h, s);          // the graph paths end with `s` waiting for the replay, so `s` orders after it
 }
 
 int hmv_synchronize(hmv_handle* h) {
     HMV_CHECK(h, "null handle");
-    HMV_CUDA(cudaSetDevice(h->cfg.device));
+    hmv::DeviceGuard guard(h->cfg.device);
     HMV_CUDA(cudaDeviceSynchronize());
     return hmv::check_flag(h);
 }
@@ -1382,7 +1441,9 @@ static int ensure_host_pipeline(hmv_handle* h, int batch) {
         }
     }
     if (batch > h->host_cap) {
-        if (h->d_bbox) { cudaFree(h->d_bbox); cudaFree(h->d_intr); cudaFree(h->d_hm); cudaFree(h->d_xy); cudaFree(h->d_j); }
+        float** bufs[5] = {&h->d_bbox, &h->d_intr, &h->d_hm, &h->d_xy, &h->d_j};
+        for (float** b : bufs) { if (*b) cudaFree(*b); *b = nullptr; }     // a failed cudaMalloc below leaves nulls, not freed addresses
+        h->host_cap = 0;
         const size_t nimg = static_cast<size_t>(batch) * h->V;
         HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_bbox), nimg * 4 * sizeof(float)));
         HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_intr), nimg * 4 * sizeof(float)));
@@ -1403,6 +1464,7 @@ static int enqueue_host(hmv_handle* h, const float* x, const float* bbox, const 
     const size_t per_sample_bytes = static_cast<size_t>(h->V) * 3 * h->img * h->img * (h->x_u8 ? 1 : sizeof(float));
     const size_t nimg = static_cast<size_t>(batch) * h->V;
     cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
+    if (hmv::ws_acquire(h, ks)) return 1;             // e.g. an hmv_forward still running on the caller's stream
     if (h->cfg.use_crop) {
         HMV_CUDA(cudaMemcpyAsync(h->d_bbox, bbox, nimg * 4 * sizeof(float), cudaMemcpyHostToDevice, ks));
         HMV_CUDA(cudaMemcpyAsync(h->d_intr, intr, nimg * 4 * sizeof(float), cudaMemcpyHostToDevice, ks));
@@ -1434,7 +1496,7 @@ static int enqueue_host(hmv_handle* h, const float* x, const float* bbox, const 
     if (heatmap) HMV_CUDA(cudaMemcpyAsync(heatmap, h->d_hm, nimg * 21 * h->hm * h->hm * sizeof(float), cudaMemcpyDeviceToHost, ks));
     if (joints_crop_img) HMV_CUDA(cudaMemcpyAsync(joints_crop_img, h->d_xy, nimg * 21 * 2 * sizeof(float), cudaMemcpyDeviceToHost, ks));
     if (joints_cam) HMV_CUDA(cudaMemcpyAsync(joints_cam, h->d_j, static_cast<size_t>(batch) * 21 * 3 * sizeof(float), cudaMemcpyDeviceToHost, ks));
-    return 0;
+    return hmv::ws_release(h, ks);
 }
 
 static int host_call_checks(hmv_handle* h, const float* x, const float* bbox, const float* intr, int batch, const char* who) {
@@ -1442,7 +1504,6 @@ static int host_call_checks(hmv_handle* h, const float* x, const float* bbox, co
     HMV_CHECK(batch >= 0, "negative batch");
     HMV_CHECK(x || batch == 0, std::string(who) + ": x is null");
     HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
-    HMV_CUDA(cudaSetDevice(h->cfg.device));
     return hmv::check_flag(h);
 }
 
@@ -1450,6 +1511,7 @@ int hmv_forward_host(hmv_handle* h, const float* x, const float* bbox, const flo
                      float* joints_crop_img, float* joints_cam) {
     if (host_call_checks(h, x, bbox, intr, batch, "hmv_forward_host")) return 1;
     if (batch == 0) return 0;
+    hmv::DeviceGuard guard(h->cfg.device);
     HMV_CHECK(h->tickets_issued == h->tickets_waited, "hmv_forward_host: asynchronous calls are still in flight (hmv_host_wait them first)");
     if (ensure_host_pipeline(h, batch)) return 1;
     if (enqueue_host(h, x, bbox, intr, batch, heatmap, joints_crop_img, joints_cam, /*ramp=*/true)) return 1;
@@ -1463,7 +1525,11 @@ int hmv_forward_host_async(hmv_handle* h, const float* x, const float* bbox, con
     if (host_call_checks(h, x, bbox, intr, batch, "hmv_forward_host_async")) return 1;
     HMV_CHECK(ticket, "hmv_forward_host_async: ticket is null");
     HMV_CHECK(batch > 0, "hmv_forward_host_async: empty batch");
-    HMV_CHECK(h->tickets_issued - h->tickets_waited < hmv_handle::kMaxInflight, "hmv_forward_host_async: too many calls in flight");
+    hmv::DeviceGuard guard(h->cfg.device);
+    while (h->tickets_issued - h->tickets_waited >= hmv_handle::kMaxInflight) {      // ring full: block on the oldest call
+        HMV_CUDA(cudaEventSynchronize(h->ev_done[h->tickets_waited % hmv_handle::kMaxInflight]));
+        ++h->tickets_waited;
+    }
     if (batch > h->host_cap && h->tickets_issued != h->tickets_waited) {      // growing the output buffers frees the old ones
         hmv::set_error("hmv_forward_host_async: batch larger than any earlier call while calls are in flight");
         return 1;
@@ -1479,8 +1545,9 @@ int hmv_forward_host_async(hmv_handle* h, const float* x, const float* bbox, con
 
 int hmv_host_wait(hmv_handle* h, int64_t ticket) {
     HMV_CHECK(h && h->prepared, "hmv_host_wait: handle not prepared");
-    HMV_CHECK(ticket >= h->tickets_waited && ticket < h->tickets_issued, "hmv_host_wait: unknown or already waited ticket (tickets complete in order)");
-    HMV_CUDA(cudaSetDevice(h->cfg.device));
+    HMV_CHECK(ticket >= 0 && ticket < h->tickets_issued, "hmv_host_wait: unknown ticket");
+    if (ticket < h->tickets_waited) return hmv::check_flag(h);      // tickets complete in issue order: this one already has
+    hmv::DeviceGuard guard(h->cfg.device);
     HMV_CUDA(cudaEventSynchronize(h->ev_done[ticket % hmv_handle::kMaxInflight]));   // the stream is in-order: earlier tickets are done too
     h->tickets_waited = ticket + 1;
     return hmv::check_flag(h);
@@ -1512,11 +1579,14 @@ int hmv_forward_u8(hmv_handle* h, const uint8_t* x, const float* bbox, const flo
     HMV_CHECK(x || batch == 0, "hmv_forward_u8: x is null");
     HMV_CHECK(!h->cfg.use_crop || (bbox && intr) || batch == 0, "'crop' positional encoding needs bbox and cam_params[\"intrinsic\"]");
     if (hmv::check_flag(h)) return 1;
+    if (batch == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (hmv::ws_acquire(h, s)) return 1;
     h->x_u8 = true;
-    const int rc = forward_eager(h, reinterpret_cast<const float*>(x), bbox, intr, batch, heatmap, joints_crop_img, joints_cam,
-                                 static_cast<cudaStream_t>(stream));
+    const int rc = forward_eager(h, reinterpret_cast<const float*>(x), bbox, intr, batch, heatmap, joints_crop_img, joints_cam, s);
     h->x_u8 = false;
-    return rc;
+    if (rc) return rc;
+    return hmv::ws_release(h, s);
 }
 
 int hmv_forward_host_u8_async(hmv_handle* h, const uint8_t* x, const float* bbox, const float* intr, int32_t batch, float* heatmap,
@@ -1534,22 +1604,37 @@ int hmv_stage_run(hmv_handle* h, int32_t stage, const float* x, const float* bbo
     HMV_CHECK(batch >= 0 && batch <= h->mb, "hmv_stage_run: batch must be <= micro_batch");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n_img = batch * h->V;
+    if (hmv::ws_acquire(h, s)) return 1;
+    int rc = 1;
     switch (stage) {
         case HMV_STAGE_BACKBONE:
             HMV_CHECK(x, "backbone stage needs x");
-            return hmv::run_backbone(h, x, n_img, -1, s);
+            rc = hmv::run_backbone(h, x, n_img, -1, s);
+            break;
         case HMV_STAGE_POSE:
-            return hmv::run_pose(h, n_img, nullptr, nullptr, s);
+            rc = hmv::run_pose(h, n_img, nullptr, nullptr, s);
+            break;
         case HMV_STAGE_SAMPLE:
             HMV_CHECK(!h->cfg.use_crop || (bbox && intr), "'crop' positional encoding needs bbox and intrinsics");
-            return h->bf16 ? hmv::run_sample_t<hmv::bf16>(h, n_img, bbox, intr, s) : hmv::run_sample_t<float>(h, n_img, bbox, intr, s);
+            rc = h->bf16 ? hmv::run_sample_t<hmv::bf16>(h, n_img, bbox, intr, s) : hmv::run_sample_t<float>(h, n_img, bbox, intr, s);
+            break;
         case HMV_STAGE_FUSION:
-            return h->bf16 ? hmv::run_fusion_t<hmv::bf16>(h, batch, s) : hmv::run_fusion_t<float>(h, batch, s);
+            rc = h->bf16 ? hmv::run_fusion_t<hmv::bf16>(h, batch, s) : hmv::run_fusion_t<float>(h, batch, s);
+            break;
         case HMV_STAGE_GCN:
-            return hmv::run_gcn(h, batch, nullptr, s);
+            rc = hmv::run_gcn(h, batch, nullptr, s);
+            break;
+        case HMV_STAGE_SOFTARGMAX:
+            ++h->launches;
+            rc = hmv::softargmax_launch(h->hm_int, h->xy, h->xy_scaled, n_img * hmv::kJoints, h->hm, h->hm, 1000.f,
+                                        static_cast<float>(h->img) / static_cast<float>(h->hm), s);
+            break;
+        default:
+            hmv::set_error("unknown stage");
+            return 1;
     }
-    hmv::set_error("unknown stage");
-    return 1;
+    if (rc) return rc;
+    return hmv::ws_release(h, s);
 }
 
 int hmv_tensor_get(hmv_handle* h, int32_t tensor, float* dst, int32_t batch, void* stream) {
@@ -1652,6 +1737,58 @@ int hmv_debug_backbone(hmv_handle* h, const float* x, int32_t n_img, int32_t num
     return 0;
 }
 
+int hmv_debug_step_io(hmv_handle* h, int32_t step, char* buf, int32_t buflen) {
+    HMV_CHECK(h && h->prepared && buf && buflen > 0, "hmv_debug_step_io: bad argument");
+    HMV_CHECK(step >= 0 && step < static_cast<int>(h->backbone.size()), "hmv_debug_step_io: bad step");
+    const hmv::Step& st = h->backbone[step];
+    std::string d;
+    for (const auto& io : st.ins) d += "in " + io.tap + " " + std::to_string(io.C) + " " + std::to_string(io.H) + " " + std::to_string(io.W) + ";";
+    for (const auto& io : st.outs) d += "out " + io.tap + " " + std::to_string(io.C) + " " + std::to_string(io.H) + " " + std::to_string(io.W) + ";";
+    HMV_CHECK(static_cast<int>(d.size()) < buflen, "hmv_debug_step_io: buffer too small");
+    memcpy(buf, d.c_str(), d.size() + 1);
+    return 0;
+}
+
+int hmv_debug_step_run(hmv_handle* h, int32_t step, int32_t n_img, const float* const* inputs, float* const* outputs,
+                       void* stream) {
+    HMV_CHECK(h && h->prepared && inputs && outputs, "hmv_debug_step_run: bad argument");
+    HMV_CHECK(step >= 0 && step < static_cast<int>(h->backbone.size()), "hmv_debug_step_run: bad step");
+    HMV_CHECK(n_img >= 1 && n_img <= h->mb_img, "hmv_debug_step_run: n_img exceeds the workspace");
+    hmv::Step& st = h->backbone[step];
+    HMV_CHECK(!st.ins.empty() && !st.outs.empty(), "hmv_debug_step_run: this step reads the network input (run it with hmv_debug_backbone)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (hmv::ws_acquire(h, s)) return 1;
+    for (size_t i = 0; i < st.ins.size(); ++i) {
+        const hmv::StepIO& io = st.ins[i];
+        HMV_CHECK(inputs[i], "hmv_debug_step_run: null input");
+        const size_t total = static_cast<size_t>(n_img) * io.C * io.H * io.W;
+        if (h->bf16) hmv::nchw_to_nhwc_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<hmv::bf16*>(io.ptr), io.C, io.H * io.W, total);
+        else hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<float*>(io.ptr), io.C, io.H * io.W, total);
+    }
+    HMV_CUDA(cudaGetLastError());
+    int rc = 1;
+    if (st.kind == hmv::SK_TAIL) rc = hmv::run_tail(h, st.layer, n_img, s);
+    else if (st.kind == hmv::SK_SEAM) rc = hmv::run_seam(h, st.layer, n_img, s);
+    else if (st.kind == hmv::SK_GEMM) rc = hmv::run_layer(h, h->layers[st.layer], n_img, s);
+    else if (st.kind == hmv::SK_MAXPOOL) {
+        ++h->launches;
+        rc = h->bf16 ? hmv::maxpool_launch<hmv::bf16>(static_cast<const hmv::bf16*>(st.in), static_cast<hmv::bf16*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s)
+                     : hmv::maxpool_launch<float>(static_cast<const float*>(st.in), static_cast<float*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s);
+    } else {
+        hmv::set_error("hmv_debug_step_run: unsupported step kind");
+    }
+    if (rc) return rc;
+    for (size_t i = 0; i < st.outs.size(); ++i) {
+        const hmv::StepIO& io = st.outs[i];
+        HMV_CHECK(outputs[i], "hmv_debug_step_run: null output");
+        const size_t total = static_cast<size_t>(n_img) * io.C * io.H * io.W;
+        if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(io.ptr), outputs[i], io.C, io.H * io.W, total);
+        else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(io.ptr), outputs[i], io.C, io.H * io.W, total);
+    }
+    HMV_CUDA(cudaGetLastError());
+    return hmv::ws_release(h, s);
+}
+
 int hmv_conv_bn_act(int32_t precision, const float* in, const float* w, const float* scale, const float* shift,
                     const float* residual, float* out, int32_t n_img, int32_t cin, int32_t hin, int32_t win,
                     int32_t cout, int32_t ksize, int32_t stride, int32_t relu, float* elapsed_ms, int32_t iters,
@@ -1750,7 +1887,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
     HMV_CUDA(cudaDeviceSynchronize());
     double ms = 0.0, fl = 0.0;
     FILE* f = csv_path ? fopen(csv_path, "w") : nullptr;
-    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops\n");
+    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops,mbytes\n");
     for (auto& r : h->prof) {
         float t = 0.f;
         cudaEventElapsedTime(&t, r.e0, r.e1);
@@ -1758,22 +1895,30 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         const double M = static_cast<double>(r.units) * L.rows_per_unit();
         const double kreal = L.kind == hmv::LK_STEM ? 147.0 : (L.kind == hmv::LK_FLAT ? static_cast<double>(L.cin) : static_cast<double>(L.cin) * L.ksize * L.ksize);
         double flop = 2.0 * M * L.cout * kreal;
+        // algorithmic HBM bytes of the launch: every input / residual / output element and every weight once
+        auto out_bytes = [&](const hmv::Layer& X, double rows) { return rows * X.cout * (X.ep.out_mode == hmv::OUT_BF16_ROWMAJOR ? 2.0 : 4.0); };
+        auto res_bytes = [&](const hmv::Layer& X, double rows) { return X.ep.res_mode == hmv::RES_NONE ? 0.0 : rows * X.cout * (X.ep.res_mode == hmv::RES_BF16 ? 2.0 : 4.0); };
+        const double in_rows = L.kind == hmv::LK_FLAT || L.ksize == 1 ? M : static_cast<double>(r.units) * L.hin * L.win;
+        double bytes = in_rows * L.cin * 2.0 + static_cast<double>(L.cout) * L.K * 2.0;
         std::string name = L.name;
         int ncol = L.cout;
         double kcol = kreal;
-        if (r.seam >= 0) {                            // fused conv3(b) + conv1(b+1)
+        if (r.seam >= 0) {                            // fused conv3(b) + conv1(b+1): conv2 output in, residual in, block output + next conv1 output out
             const hmv::Layer& L1 = h->layers[h->seams[r.seam].l1];
             flop += 2.0 * M * L1.cout * L1.cin;
+            bytes += out_bytes(L, M) + res_bytes(L, M) + out_bytes(L1, M) + static_cast<double>(L1.cout) * L1.K * 2.0;
             name = L.name + "+next.conv1";
-        }
-        if (r.tail >= 0) {                            // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3
+        } else if (r.tail >= 0) {                     // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3 (the conv2 output stays on chip / in L2)
             const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
             flop += 2.0 * M * L3.cout * L3.cin;
+            bytes += out_bytes(L3, M) + res_bytes(L3, M) + static_cast<double>(L3.cout) * L3.K * 2.0;
             name = L.name + "+conv3";
             ncol = L3.cout; kcol = kreal + L3.cin;
+        } else {
+            bytes += out_bytes(L, M) + res_bytes(L, M);
         }
         ms += t; fl += flop;
-        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12);
+        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f,%.3f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12, bytes * 1e-6);
         h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
     }
     if (f) fclose(f);

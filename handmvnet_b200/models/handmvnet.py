@@ -171,6 +171,15 @@ class HostTicket:
             self._pool = None
         return out
 
+    def __del__(self):
+        # a ticket dropped without result(): its pinned buffers must outlive the copies still in flight on the
+        # library's private streams (torch's pinned allocator does not know about those streams)
+        try:
+            if not self._done and self._model._handle is not None:
+                _lib.load().hmv_host_wait(self._model._handle, self._ticket)
+        except Exception:  # interpreter shutdown
+            pass
+
 
 class HandMvNet(nn.Module):
     """`HandMvNet(train_params, model_params, data_params)` - reference handmvnet.py:28.
@@ -245,6 +254,7 @@ class HandMvNet(nn.Module):
         self.micro_batch = int(micro_batch)
         self._handle = None
         self._handle_device = None
+        self._input_norm = None              # (mean, std) for uint8 inputs; None = the library's ImageNet defaults
 
     # ---- Lightning API used by the reference drivers (eval_fps.py:64-65, eval.py:86-87) ----------
     def freeze(self):
@@ -255,14 +265,16 @@ class HandMvNet(nn.Module):
     # ---- handle management -------------------------------------------------------------------------
     def _release(self):
         if self._handle is not None:
-            _lib.load().hmv_destroy(self._handle)
-            self._handle = None
-            self._handle_device = None
+            handle, self._handle, self._handle_device = self._handle, None, None
+            _lib.check(_lib.load().hmv_destroy(handle), "hmv_destroy")
 
     def __del__(self):
         try:
             self._release()
-        except Exception:
+        except RuntimeError as e:            # a failing hmv_destroy must not be silent
+            import warnings
+            warnings.warn(f"handmvnet_b200: {e}")
+        except Exception:                    # interpreter shutdown: modules may already be gone
             pass
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -311,6 +323,8 @@ class HandMvNet(nn.Module):
                 raise
         self._handle = handle
         self._handle_device = torch.device("cuda", index)
+        if self._input_norm is not None:     # survives .to() / load_state_dict(), which rebuild the handle
+            self._apply_input_norm()
         return self
 
     def _ensure(self, device):
@@ -319,6 +333,8 @@ class HandMvNet(nn.Module):
             raise RuntimeError("handmvnet_b200 forward needs CUDA tensors (no CPU fallback); use forward_host() "
                                "for host buffers")
         index = device.index if device.index is not None else torch.cuda.current_device()
+        if self.training:                    # .train() after prepare(): BatchNorm batch statistics / dropout are not built
+            raise RuntimeError("handmvnet_b200 implements the inference path only: call .eval() / .freeze() first")
         if self._handle is None or self._handle_device.index != index:
             self.prepare(torch.device("cuda", index))
         return self._handle
@@ -456,8 +472,17 @@ class HandMvNet(nn.Module):
 
     def set_input_norm(self, mean, std):
         """Per-channel mean / std applied to uint8 inputs (defaults: the reference's ImageNet constants, datasets/ho3d.py:35-40)."""
-        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
-        sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+        mean, std = [float(v) for v in mean], [float(v) for v in std]
+        if len(mean) != 3 or len(std) != 3 or min(std) <= 0:
+            raise ValueError("mean / std must have 3 entries, std > 0")
+        self._input_norm = (mean, std)       # kept on the module: re-applied whenever the handle is rebuilt
+        if self._handle is not None:
+            self._apply_input_norm()
+
+    def _apply_input_norm(self):
+        mean, std = self._input_norm
+        m = (ctypes.c_float * 3)(*mean)
+        sd = (ctypes.c_float * 3)(*std)
         _lib.check(_lib.load().hmv_set_input_norm(self._handle, m, sd), "hmv_set_input_norm")
 
     def synchronize(self):
@@ -515,6 +540,39 @@ class HandMvNet(nn.Module):
                                                       stream), "hmv_debug_backbone")
         c, hh, ww = chw[0], chw[1], chw[2]
         return buf[: n_img * c * hh * ww].view(n_img, c, hh, ww)
+
+    def debug_step_io(self, step):
+        """([(tap, C, H, W)] inputs, [(tap, C, H, W)] outputs) of backbone plan step `step`; the taps are the keys of
+        oracle.backbone(per_layer=True).  An empty input list means the step reads the network input."""
+        buf = ctypes.create_string_buffer(1024)
+        _lib.check(_lib.load().hmv_debug_step_io(self._handle, step, buf, 1024), "hmv_debug_step_io")
+        ins, outs = [], []
+        for item in buf.value.decode().split(";"):
+            if not item:
+                continue
+            kind, tap, c, hh, ww = item.split(" ")
+            (ins if kind == "in" else outs).append((tap, int(c), int(hh), int(ww)))
+        return ins, outs
+
+    def debug_step_run(self, step, inputs):
+        """Run backbone plan step `step` alone on teacher-forced inputs (NCHW fp32 tensors in debug_step_io order);
+        returns its outputs as NCHW fp32 tensors."""
+        dev = self._handle_device
+        ins, outs = self.debug_step_io(step)
+        if len(inputs) != len(ins):
+            raise ValueError(f"step {step} takes {len(ins)} inputs")
+        inputs = [self._f32(t, dev) for t in inputs]
+        n_img = inputs[0].shape[0]
+        for t, (tap, c, hh, ww) in zip(inputs, ins):
+            if tuple(t.shape) != (n_img, c, hh, ww):
+                raise ValueError(f"{tap}: expected {(n_img, c, hh, ww)}, got {tuple(t.shape)}")
+        results = [torch.empty((n_img, c, hh, ww), device=dev, dtype=torch.float32) for _, c, hh, ww in outs]
+        pin = (ctypes.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+        pout = (ctypes.c_void_p * len(results))(*[t.data_ptr() for t in results])
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.load().hmv_debug_step_run(self._handle, step, n_img, pin, pout, stream), "hmv_debug_step_run")
+        return results
 
     def profile(self, enable: bool):
         _lib.check(_lib.load().hmv_profile_enable(self._handle, int(enable)), "hmv_profile_enable")

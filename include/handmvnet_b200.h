@@ -104,7 +104,8 @@ enum {
     HMV_STAGE_POSE = 1,       /* handmvnet.py:180-182    FEAT -> HEATMAP, XY                */
     HMV_STAGE_SAMPLE = 2,     /* handmvnet.py:185-225 + layers.py:157  FEAT, XY -> TOKENS   */
     HMV_STAGE_FUSION = 3,     /* fusion.py:26-30         TOKENS -> FUSED                    */
-    HMV_STAGE_GCN = 4         /* nets.py:133-139         FUSED -> JOINTS                    */
+    HMV_STAGE_GCN = 4,        /* nets.py:133-139         FUSED -> JOINTS                    */
+    HMV_STAGE_SOFTARGMAX = 5  /* models/utils.py:35-62   HEATMAP -> XY (soft_argmax_2d alone) */
 };
 enum {
     HMV_T_FEAT = 0,           /* [n*V, 1024, 32, 32] NCHW                                    */
@@ -128,6 +129,14 @@ int hmv_debug_backbone(hmv_handle* h, const float* x, int32_t n_img, int32_t num
                        int32_t* chw, void* stream);
 int hmv_debug_num_steps(hmv_handle* h);
 const char* hmv_debug_step_name(hmv_handle* h, int32_t step);
+/* One backbone plan step alone, TEACHER-FORCED (per-kernel parity of the fused bottleneck kernels against
+ * backbones/resnet.py:124-144): hmv_debug_step_io describes the activations the step reads and writes as
+ * "in <oracle tap> C H W;...;out <oracle tap> C H W;" (empty "in" list: the step reads the network input and
+ * cannot be forced); hmv_debug_step_run imports `inputs[i]` (NCHW fp32 device buffers, in the order listed),
+ * runs the step's kernel and exports every output to `outputs[i]` (NCHW fp32). */
+int hmv_debug_step_io(hmv_handle* h, int32_t step, char* buf, int32_t buflen);
+int hmv_debug_step_run(hmv_handle* h, int32_t step, int32_t n_img, const float* const* inputs,
+                       float* const* outputs, void* stream);
 
 /* One implicit-GEMM convolution through the same kernels the model uses (micro-benchmark /
  * kernel unit test):  out = act(conv(in, w) * scale + shift (+ residual)),  NCHW fp32 in/out,

@@ -249,8 +249,8 @@ def soft_argmax_2d(heatmap, temperature: float = 1000.0):
     p = F.softmax(heatmap.reshape(n, j, -1) * temperature, dim=2).reshape(n, j, h, w)
     px = p.sum(dim=2)          # marginal over rows  -> [n,j,w]
     py = p.sum(dim=3)          # marginal over cols  -> [n,j,h]
-    ex = (px * torch.arange(w, dtype=torch.float32)[None, None]).sum(dim=2, keepdim=True)
-    ey = (py * torch.arange(h, dtype=torch.float32)[None, None]).sum(dim=2, keepdim=True)
+    ex = (px * torch.arange(w, dtype=torch.float32, device=heatmap.device)[None, None]).sum(dim=2, keepdim=True)
+    ey = (py * torch.arange(h, dtype=torch.float32, device=heatmap.device)[None, None]).sum(dim=2, keepdim=True)
     return torch.cat((ex, ey), dim=2)
 
 
@@ -304,6 +304,19 @@ def crop_fov(bbox, intr):
     return torch.stack((tx, ty), dim=2).flatten(start_dim=-2)   # [n, 10]
 
 
+_CONST_CACHE = {}
+
+
+def _const(key, device, build):
+    """Constant tables live on the tensor's device and are built once (the reference re-copies `pe` and re-derives the
+    Chebyshev basis on the CPU every forward, layers.py:157,393-394; caching only favours the baseline when the oracle is
+    timed as eager PyTorch on a GPU)."""
+    k = (key, str(device))
+    if k not in _CONST_CACHE:
+        _CONST_CACHE[k] = build().to(device)
+    return _CONST_CACHE[k]
+
+
 def positional_table(d_model: int, max_len: int):
     """reference layers.py:136-150 (even and odd d_model)."""
     pos = torch.arange(max_len).unsqueeze(1)
@@ -345,7 +358,8 @@ def fusion(sd, tokens, num_layers=5, add_pos=True, query_len=NUM_JOINTS, taps=No
     query the rest), (L-1)/2 self."""
     x = tokens
     if add_pos:
-        x = x + positional_table(x.shape[-1], x.shape[1])[None]
+        d_model, n_tok = x.shape[-1], x.shape[1]
+        x = x + _const(("pe", d_model, n_tok), x.device, lambda: positional_table(d_model, n_tok))[None]
     if taps is not None:
         taps["tokens_pe"] = x
     half = (num_layers - 1) // 2
@@ -384,7 +398,7 @@ def cheb_basis(order: int = 3):
 
 def gcn_decoder(sd, x, taps=None):
     """reference nets.py:133-139: ChebConv(K=2) x3 with LeakyReLU(0.01) after 1 and 2."""
-    t = cheb_basis(3).unsqueeze(1)                       # [3,1,21,21]
+    t = _const("cheb3", x.device, lambda: cheb_basis(3)).unsqueeze(1)   # [3,1,21,21]
     for i in (1, 2, 3):
         w = sd[f"joints_decoder.joints_gcn{i}.weight"]   # [3,1,cin,cout]
         r = torch.matmul(torch.matmul(t, x), w)          # [3,B,21,cout]
@@ -402,16 +416,23 @@ def gcn_decoder(sd, x, taps=None):
 @torch.no_grad()
 def forward(sd, cfg, x, bbox=None, intr=None, return_taps=False, teacher=None):
     """Returns the reference's output dict; with return_taps also every stage tensor.
-    `teacher` may override a stage input by name (used for teacher-forced parity)."""
+    `teacher` may override a stage input by name ("backbone_out", "coords"): teacher-forced parity - everything
+    downstream of the override is computed from it (soft-argmax at T=1000 is discontinuous, so the
+    end-to-end bf16 check conditions both sides on the same joint coordinates)."""
     taps = OrderedDict() if return_taps else None
     b, v, c, h, w = x.shape
     nv = cfg["model"]["num_views"]
     if v != nv:
         raise ValueError(f"input has {v} views, model was built for {nv}")
     pe_list = cfg["model"].get("pos_enc", ["pos2d", "sin"])
+    teacher = teacher or {}
     feat = backbone(sd, x.reshape(-1, c, h, w), taps)
+    if "backbone_out" in teacher:                        # [b*v, 1024, 32, 32]
+        feat = teacher["backbone_out"]
     hm = pose_net(sd, feat, taps)
     xy = soft_argmax_2d(hm)
+    if "coords" in teacher:                              # [b*v, 21, 2] heat-map pixels: conditions everything downstream
+        xy = teacher["coords"].reshape(xy.shape).to(xy.dtype)
     sampled = sample_net(sd, feat, xy, taps)
     tok = sampled
     if "pos2d" in pe_list:
