@@ -107,6 +107,7 @@ class ClockSampler:
                 "sm_max_mhz": getattr(self, "max_sm", None), "reasons": reasons,
                 "power_w_max": max((r[2] for r in rows), default=None), "samples": len(rows),
                 "samples_total": len(self.rows), "query_ms_max": max((r[4] for r in self.rows), default=0.0) * 1e3,
+                "query_ms_max_in_region": max((r[4] for r in rows), default=0.0) * 1e3,
                 "source": f"NVML, {self.period * 1e3:.0f} ms period, timed region only", "error": self.error}
 
 

@@ -36,7 +36,7 @@ def main():
             d["us"] = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
         else:
             d[r["Metric Name"]] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-    order = [launches[k] for k in sorted(launches)]
+    order = [launches[k] for k in sorted(launches) if "hmv::" in launches[k]["name"]]     # torch's own kernels (input generation, isfinite) are not part of a step
     assert len(order) % nsteps == 0, f"{len(order)} launches do not split into {nsteps} identical steps"
     per = len(order) // nsteps
     step = order[-per:]
