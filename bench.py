@@ -218,8 +218,11 @@ def run_own(args, lines):
     barrier()
     launches0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    import gc
+    gc.collect()
+    gc.disable()              # a generation-2 collection inside the timed loop stalls the enqueueing thread for tens of ms
+    barrier()
     t_region0 = time.perf_counter()
     e0.record()
     marks[0].record()
@@ -231,6 +234,7 @@ def run_own(args, lines):
     e1.record()
     barrier()
     t_region1 = time.perf_counter()
+    gc.enable()
     dev_ms = e0.elapsed_time(e1)
     step_ms = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     launches = model.launch_count() - launches0

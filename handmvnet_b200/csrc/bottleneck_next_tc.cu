@@ -23,9 +23,6 @@
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
-#include <map>
-#include <utility>
-
 namespace hmv {
 
 namespace {
@@ -56,17 +53,25 @@ __device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
     return true;
 }
 
-// CL = 2 (opt-in, HMV_SEAM_CLUSTER=1): clusters of two CTAs on neighbouring M tiles; every weight tile (W3 chunk K block,
-// W1 K block) is loaded half by each CTA and multicast into both, so the weights cross L2 -> SM once per pair (the
-// timing model in tools/seam_timing_model.py puts the kernel on the SM's TMA fill bandwidth).  tmW3 / tmW1 then carry
-// half-height boxes; an operand stage is refilled only after BOTH CTAs consumed it (`empty` count 2, multicast commit).
-template <int CL>
+// mbar_wait that also accumulates the stall time (clock cycles) into `acc` when PROF (HMV_BN_PROF=1 runs)
+template <bool PROF>
+__device__ __forceinline__ bool bn_wait(uint32_t bar, uint32_t parity, int* err_flag, int code, long long& acc) {
+    if (!PROF) return mbar_wait(bar, parity, err_flag, code);
+    const long long t0 = clock64();                  // (try_wait may suspend inside the instruction: time it as well)
+    const bool ok = mbar_wait(bar, parity, err_flag, code);
+    acc += clock64() - t0;
+    return ok;
+}
+
+// (A 2-CTA cluster variant with multicast weight tiles was measured at -1 % in round 1 - the kernel is not bound by the
+// L2 -> SM fill bandwidth - and has been removed.)
+template <bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 output [rows, 256], load box {64, 128}
-                       const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}  (CL = 2: {64, 64})
+                       const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}  
                        const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 1024], load box {64, 128}
                        const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 32}
-                       const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}  (CL = 2: {64, 128})
+                       const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}  
                        const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
                        const __grid_constant__ BnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -88,13 +93,12 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY2); prefetch_tmap(&tmW3); prefetch_tmap(&tmRes); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmY1);
         for (int i = 0; i < kBnStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, CL);                  // one commit per CTA of the cluster
+            mbar_init(empty0 + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(t3full0 + 8 * i, 1);
@@ -116,60 +120,50 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();   // the peer's barriers exist before anything remote lands on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
     pdl_launch_dependents();
 
-    // CL == 1: this CTA's tiles are blockIdx.x, + gridDim.x, ...   CL == 2: the cluster walks pairs of M tiles and this
-    // CTA takes tile 2 * pair + rank; a tile past the end is a dummy (zero-filled loads, clipped stores).
-    const int units = CL == 2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
-    const int first = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int step = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    const int n_i = (units - first + step - 1) / step;
-    auto tile_of = [&](int i) { return CL == 2 ? 2 * (first + i * step) + static_cast<int>(crank) : first + i * step; };
+    // this CTA's tiles are blockIdx.x, + gridDim.x, ...
+    const int first = static_cast<int>(blockIdx.x), step = static_cast<int>(gridDim.x);
+    const int n_i = (p.num_m_tiles - first + step - 1) / step;
+    auto tile_of = [&](int i) { return first + i * step; };
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring (same order as the MMA issuer consumes it) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            long long w_e3 = 0, w_e1 = 0;
             for (int i = 0; i < n_i; ++i) {
                 const int m = tile_of(i);
                 const bool ok = bn_tile_schedule(
                     [&](int c) {
                         for (int kb = 0; kb < kBnKb3; ++kb) {
-                            if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51)) return false;
+                            if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51, w_e3)) return false;
                             const uint32_t fb = full0 + 8 * stage;
                             const uint32_t sa = smem_base + stage * kBnStageBytes;
                             mbar_arrive_expect_tx(fb, kBnStageBytes);
                             tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
-                            if (CL == 2)
-                                tma_load_2d_mc(sa + kBnStageBytes / 2 + crank * (kBnStageBytes / 4), &tmW3, fb, kb * kTcBlockK,
-                                               c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2), static_cast<uint16_t>(3));
-                            else
-                                tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
                     },
                     [&](int c) {
                         for (int j = 0; j < 2; ++j) {
-                            if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52)) return false;
+                            if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52, w_e1)) return false;
                             const uint32_t fb = full0 + 8 * stage;
                             mbar_arrive_expect_tx(fb, kBnStageBytes);
-                            if (CL == 2)
-                                tma_load_2d_mc(smem_base + stage * kBnStageBytes + crank * (kBnStageBytes / 2), &tmW1, fb,
-                                               (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2), static_cast<uint16_t>(3));
-                            else
-                                tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
                     });
                 if (!ok) break;
             }
+            if (PROF && p.prof) { p.prof[blockIdx.x * 24 + 6] = w_e3; p.prof[blockIdx.x * 24 + 7] = w_e1; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -180,16 +174,18 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q3 = 0;                                 // running conv3 chunk counter (TMEM slot = q3 & 1)
+            long long w_t3e = 0, w_f3 = 0, w_t1e = 0, w_ar = 0, w_f1 = 0;
+            const long long t_start = clock64();
             for (int i = 0; i < n_i; ++i) {
                 const uint32_t gbase = static_cast<uint32_t>(i) * kBnSlotsPerTile;
                 const bool ok = bn_tile_schedule(
                     [&](int) {
                         const uint32_t s = q3 & 1u, use = q3 >> 1;
-                        if (!mbar_wait(t3empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 53)) return false;
+                        if (!bn_wait<PROF>(t3empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 53, w_t3e)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBnP + s * kBnChunk;
                         for (int kb = 0; kb < kBnKb3; ++kb) {
-                            if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 54)) return false;
+                            if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 54, w_f3)) return false;
                             tc_fence_after();
                             const uint32_t sa = smem_base + stage * kBnStageBytes;
                             const uint32_t sb = sa + kBnStageBytes / 2;
@@ -197,8 +193,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
                                 umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
                                          (kb | k) != 0 ? 1u : 0u);
-                            if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));
-                            else umma_commit(empty0 + 8 * stage);
+                            umma_commit(empty0 + 8 * stage);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         umma_commit(t3full0 + 8 * s);
@@ -209,10 +204,10 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t g = gbase + 2 * c + j, slot = g % kBnSlots, use = g / kBnSlots;
                             if (c == 0 && j == 0) {          // acc1 drained by the epilogue of the previous tile
-                                if (!mbar_wait(t1empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, p.err_flag, 55)) return false;
+                                if (!bn_wait<PROF>(t1empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, p.err_flag, 55, w_t1e)) return false;
                             }
-                            if (!mbar_wait(aready0 + 8 * slot, use & 1u, p.err_flag, 56)) return false;
-                            if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 57)) return false;
+                            if (!bn_wait<PROF>(aready0 + 8 * slot, use & 1u, p.err_flag, 56, w_ar)) return false;
+                            if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 57, w_f1)) return false;
                             tc_fence_after();
                             const uint32_t sa = slots_base + slot * kBnSlotBytes;          // finished block-output chunk = A operand
                             const uint32_t sb = smem_base + stage * kBnStageBytes;
@@ -220,8 +215,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
                                 umma_f16(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
                                          (c | j | k) != 0 ? 1u : 0u);
-                            if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));
-                            else umma_commit(empty0 + 8 * stage);
+                            umma_commit(empty0 + 8 * stage);
                             umma_commit(sfree0 + 8 * slot);                                // the slot's MMAs have retired
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
@@ -230,6 +224,10 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     });
                 if (!ok) break;
             }
+            if (PROF && p.prof) {
+                long long* o = p.prof + blockIdx.x * 24;
+                o[0] = clock64() - t_start; o[1] = w_t3e; o[2] = w_f3; o[3] = w_t1e; o[4] = w_ar; o[5] = w_f1; o[15] = n_i;
+            }
         }
         __syncwarp();
     } else if (warp == 2) {
@@ -237,11 +235,12 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         if (lane == 0) {
             uint32_t g = 0;
             bool alive = true;
+            long long w_sf = 0;
             for (int i = 0; i < n_i && alive; ++i) {
                 const int m = tile_of(i);
                 for (int c = 0; c < kBnSlotsPerTile && alive; ++c, ++g) {
                     const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
-                    if (!mbar_wait(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58)) { alive = false; break; }
+                    if (!bn_wait<PROF>(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58, w_sf)) { alive = false; break; }
                     if (c < 2 * kBnNch) {
                         mbar_arrive_expect_tx(sres0 + 8 * slot, kBnSlotBytes);
                         tma_load_2d(slots_base + slot * kBnSlotBytes, &tmRes, sres0 + 8 * slot, c * kBnSlotCols, m * kTcBlockM);
@@ -251,6 +250,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     }
                 }
             }
+            if (PROF && p.prof) p.prof[blockIdx.x * 24 + 8] = w_sf;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -263,6 +263,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         uint32_t g = 0;
         int pending = -1;                                    // issuer: slot whose TMA store may still be reading smem
         bool alive = true;
+        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_nb = 0, w_bulk = 0, w_ldt = 0;
+        const long long e_start = clock64();
 
         auto do_slot = [&](uint32_t tcol, const float* bias, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
             const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
@@ -271,7 +273,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             float4 bq[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + j);
-            if (!mbar_wait(sres0 + 8 * slot, use & 1u, p.err_flag, 59)) alive = false;
+            if (!bn_wait<PROF>(sres0 + 8 * slot, use & 1u, p.err_flag, 59, w_sres)) alive = false;
             uint8_t* srow = slots + slot * kBnSlotBytes + slab_off;
             uint4 rq[4];
             if (is_conv3) {
@@ -279,7 +281,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                 for (int j = 0; j < 4; ++j)
                     rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
             }
-            tmem_ld_wait();
+            if (PROF) { const long long t0 = clock64(); tmem_ld_wait(); w_ldt += clock64() - t0; } else tmem_ld_wait();
             if (release_bar != 0) {                          // accumulator fully read: hand TMEM back early
                 tc_fence_before();
                 __syncwarp();
@@ -303,12 +305,13 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             fence_async_smem();                              // generic-proxy writes -> visible to the TMA store and to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(aready0 + 8 * slot);  // every slot use (conv1 slots too: keeps the barrier's phase == use count)
-            named_bar_sync(1 + quarter, 64);                 // both column halves of this quarter's slab are written
+            if (PROF) { const long long t0 = clock64(); named_bar_sync(1 + quarter, 64); w_nb += clock64() - t0; }
+            else named_bar_sync(1 + quarter, 64);            // both column halves of this quarter's slab are written
             if (issuer) {
                 tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
                 bulk_commit();
                 if (pending >= 0) {                          // the previous store has left shared memory
-                    bulk_wait_read<1>();
+                    if (PROF) { const long long t0 = clock64(); bulk_wait_read<1>(); w_bulk += clock64() - t0; } else bulk_wait_read<1>();
                     mbar_arrive(sfree0 + 8 * pending);
                 }
                 pending = static_cast<int>(slot);
@@ -321,7 +324,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             const int m = tile_of(i);
             for (int c = 0; c < kBnNch && alive; ++c, ++q3) {
                 const uint32_t s = q3 & 1u;
-                if (!mbar_wait(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60)) { alive = false; break; }
+                if (!bn_wait<PROF>(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60, w_t3f)) { alive = false; break; }
                 tc_fence_after();
 #pragma unroll 1
                 for (int cc = 0; cc < 2 && alive; ++cc)
@@ -329,7 +332,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             cc == 1 ? t3empty0 + 8 * s : 0u, &tmOut, c * kBnChunk + cc * kBnSlotCols, m * kTcBlockM);
             }
             if (!alive) break;
-            if (!mbar_wait(t1full, static_cast<uint32_t>(i) & 1u, p.err_flag, 61)) { alive = false; break; }
+            if (!bn_wait<PROF>(t1full, static_cast<uint32_t>(i) & 1u, p.err_flag, 61, w_t1f)) { alive = false; break; }
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < kBnP / kBnSlotCols && alive; ++cc)
@@ -337,12 +340,15 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         cc * kBnSlotCols, m * kTcBlockM);
         }
         if (issuer) bulk_wait_read<0>();                     // staged data must stay valid until every store has read it
+        if (PROF && p.prof && warp == 4 && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 24;
+            o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = w_nb; o[14] = w_bulk; o[16] = w_ldt;
+        }
         __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();   // the peer may still multicast into this CTA / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -352,39 +358,20 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 }  // namespace
 
 int bn_init() {
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
     return 0;
 }
 
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0) return 0;
-    if (l.cluster == 2) {              // tmW3 / tmW1 carry half-height boxes
-        static std::map<std::pair<int, int>, int> cache;                   // per (device, persistent-grid cap)
-        int dev = 0;
-        HMV_CUDA(cudaGetDevice(&dev));
-        int& max_clusters = cache.emplace(std::make_pair(dev, num_sms), -1).first->second;
-        if (max_clusters < 0) {        // the persistent grid must be co-resident; clusters are placed inside one GPC
-            cudaLaunchConfig_t qc{};
-            qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = kBnSmemBytes;
-            cudaLaunchAttribute qa[1];
-            qa[0].id = cudaLaunchAttributeClusterDimension;
-            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-            qc.attrs = qa; qc.numAttrs = 1;
-            int n = 0;
-            HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, bottleneck_next_kernel<2>, &qc));
-            HMV_CHECK(n > 0, "no 2-CTA cluster of the seam kernel fits on this device");
-            max_clusters = n < num_sms / 2 ? n : num_sms / 2;
-        }
-        const int pairs = (l.p.num_m_tiles + 1) / 2;
-        const int clusters = pairs < max_clusters ? pairs : max_clusters;
-        HMV_CUDA(launch_kernel_cluster(bottleneck_next_kernel<2>, dim3(2 * clusters), dim3(kTcThreads), 2, kBnSmemBytes, stream, l.tmY2,
-                                       l.tmW3, l.tmRes, l.tmOut, l.tmW1, l.tmY1, l.p));
-        return 0;
-    }
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
-    HMV_CUDA(launch_kernel(bottleneck_next_kernel<1>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
-                           l.tmW1, l.tmY1, l.p));
+    if (l.p.prof)
+        HMV_CUDA(launch_kernel(bottleneck_next_kernel<true>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
+                               l.tmW1, l.tmY1, l.p));
+    else
+        HMV_CUDA(launch_kernel(bottleneck_next_kernel<false>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
+                               l.tmW1, l.tmY1, l.p));
     return 0;
 }
 

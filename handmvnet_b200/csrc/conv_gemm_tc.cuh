@@ -90,11 +90,11 @@ struct BnParams {
     const float* bias3;                // [1024] folded BN of conv3 (block b)
     const float* bias1;                // [256]  folded BN of conv1 (block b+1)
     int* err_flag;
+    long long* prof;                   // optional [grid][24] stall counters (HMV_BN_PROF=1), else null
 };
 struct BnLaunch {
     CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;
     BnParams p;
-    int cluster;                       // 1, or 2: CTA pairs with multicast weight tiles (tmW3 / tmW1 are half-height boxes)
 };
 int bn_init();
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream);

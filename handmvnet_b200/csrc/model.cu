@@ -155,7 +155,6 @@ struct hmv_handle {
     std::vector<FusedTail> tails;
     std::vector<FusedSeam> seams;
     bool fuse_next = true;                        // HMV_FUSE_NEXT=0: layer3 conv3(b) and conv1(b+1) as separate kernels
-    bool seam_cluster = false;                    // HMV_SEAM_CLUSTER=1: the seam kernel as 2-CTA clusters with multicast weights
     int fuse_mask = 3;                            // bottleneck widths whose conv2+conv3 run fused: bit0 P=64, bit1 P=128, bit2 P=256 (HMV_FUSE_TAIL=<mask>)
     std::vector<FusionLayerPlan> fusion;
     int pose0 = -1, pose3 = -1, samp = -1;
@@ -524,6 +523,28 @@ static int run_seam(hmv_handle* h, int seam, int units, cudaStream_t s) {
     ++h->launches;
     BnLaunch b = S.bn;
     b.p.num_m_tiles = units * L3.rows_per_unit() / kTcBlockM;
+    static const bool bn_prof = [] { const char* e = getenv("HMV_BN_PROF"); return e && e[0] == '1'; }();
+    if (bn_prof) {                                    // bring-up aid: per-role stall cycles of one launch, printed to stderr
+        static long long* dbuf = nullptr;
+        static int printed = 0;
+        if (!dbuf) HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 148 * 24 * sizeof(long long)));
+        HMV_CUDA(cudaMemsetAsync(dbuf, 0, 148 * 24 * sizeof(long long), s));
+        b.p.prof = dbuf;
+        const int rc = bn_launch(b, h->num_sms, s);
+        if (rc == 0 && units >= 64 && printed < 10) {
+            std::vector<long long> host(148 * 24);
+            HMV_CUDA(cudaStreamSynchronize(s));
+            HMV_CUDA(cudaMemcpy(host.data(), dbuf, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double a[24] = {0};
+            const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) a[k] += static_cast<double>(host[c * 24 + k]) / grid;
+            fprintf(stderr, "[bn_prof] %s tiles/cta %.1f | mma total %.0f: t3empty %.0f full3 %.0f t1empty %.0f aready %.0f full1 %.0f | prod: empty3 %.0f empty1 %.0f | "
+                    "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f namedbar %.0f bulk %.0f tmem_ld %.0f (cycles, mean over CTAs)\n",
+                    S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]);
+            ++printed;
+        }
+        return rc;
+    }
     if (!h->profiling) return bn_launch(b, h->num_sms, s);
     cudaEvent_t ev[2];
     for (int i = 0; i < 2; ++i) {
@@ -679,10 +700,8 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
     BnLaunch& b = S.bn;
     memset(&b.p, 0, sizeof(b.p));
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
-    const bool seam_cluster = h->seam_cluster;        // opt-in (HMV_SEAM_CLUSTER=1)
-    b.cluster = seam_cluster ? 2 : 1;
-    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, seam_cluster ? 64 : 128) ||
-        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, seam_cluster ? 128 : 256)) {
+    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, 128) ||
+        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, 256)) {
         set_error(std::string(get_error()) + " [fused-seam maps of " + name + "]");
         return 1;
     }
@@ -1197,8 +1216,6 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     {
         const char* e = getenv("HMV_FUSE_NEXT");
         h->fuse_next = !(e && e[0] == '0');
-        const char* c = getenv("HMV_SEAM_CLUSTER");
-        h->seam_cluster = c && c[0] == '1';
     }
     {
         const char* u = getenv("HMV_FUSION_UNFUSED");
