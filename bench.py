@@ -57,6 +57,7 @@ class ClockSampler:
     def __init__(self, gpu_index, period_s=0.02):
         self.rows, self.idx, self.period = [], gpu_index, period_s
         self._stop = threading.Event()
+        self._active = threading.Event()       # queries run only while set (see resume / pause)
         self._thread = None
         self.error = None
 
@@ -79,6 +80,8 @@ class ClockSampler:
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             mode = os.environ.get("HMV_BENCH_SAMPLER", "full")
             while not self._stop.is_set():
+                if not self._active.wait(timeout=0.05):
+                    continue
                 t = time.perf_counter()
                 clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0 if mode != "clock" else 0.0
@@ -92,6 +95,16 @@ class ClockSampler:
     def start(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
+
+    # NVML queries from a second thread were measured to stall the thread that enqueues CUDA work for 50-140 ms every
+    # few runs (4 of 7 runs with the sampler, 0 of 3 without: profiles/r02/README.md), which empties the GPU queue in the
+    # middle of the timed region.  The sampler therefore runs only between resume() - called once all K timed steps
+    # are enqueued, i.e. while the GPU is still working through them - and pause() at the end of the region.
+    def resume(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
 
     def stop(self, t_begin=None, t_end=None):
         """Summary over the samples taken in [t_begin, t_end] (perf_counter seconds): the timed region."""
@@ -108,7 +121,7 @@ class ClockSampler:
                 "power_w_max": max((r[2] for r in rows), default=None), "samples": len(rows),
                 "samples_total": len(self.rows), "query_ms_max": max((r[4] for r in self.rows), default=0.0) * 1e3,
                 "query_ms_max_in_region": max((r[4] for r in rows), default=0.0) * 1e3,
-                "source": f"NVML, {self.period * 1e3:.0f} ms period, timed region only", "error": self.error}
+                "source": f"NVML, {self.period * 1e3:.0f} ms period, during the timed region (from the moment its last step is enqueued)", "error": self.error}
 
 
 def cpu_oracle_throughput(batch, iters, warmup, views=5):
@@ -232,8 +245,10 @@ def run_own(args, lines):
         marks[i + 1].record()
     enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / args.steps
     e1.record()
+    sampler.resume()          # the steps are enqueued; the GPU executes them while the clocks are sampled
     barrier()
     t_region1 = time.perf_counter()
+    sampler.pause()
     gc.enable()
     dev_ms = e0.elapsed_time(e1)
     step_ms = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))

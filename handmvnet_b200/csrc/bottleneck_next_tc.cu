@@ -108,7 +108,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         mbar_init(t1empty, 8);
         for (int i = 0; i < kBnSlots; ++i) {
             mbar_init(sres0 + 8 * i, 1);
-            mbar_init(aready0 + 8 * i, 8);
+            mbar_init(aready0 + 8 * i, 4);                   // the four slab warps of the team that handles the slot
             mbar_init(sfree0 + 8 * i, 5);                   // 4 slab-store issuers + the MMA commit (conv3 slots) / the slot producer (conv1 slots)
         }
         fence_barrier_init();
@@ -138,6 +138,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             long long w_e3 = 0, w_e1 = 0;
             for (int i = 0; i < n_i; ++i) {
                 const int m = tile_of(i);
+                if (p.prefetch && i + 1 < n_i)               // next tile's conv2 output: HBM -> L2 a whole tile ahead of its ring loads
+                    for (int kb = 0; kb < kBnKb3; ++kb) tma_prefetch_l2_2d(&tmY2, kb * kTcBlockK, tile_of(i + 1) * kTcBlockM);
                 const bool ok = bn_tile_schedule(
                     [&](int c) {
                         for (int kb = 0; kb < kBnKb3; ++kb) {
@@ -238,6 +240,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             long long w_sf = 0;
             for (int i = 0; i < n_i && alive; ++i) {
                 const int m = tile_of(i);
+                if (p.prefetch && i + 1 < n_i)               // next tile's residual: HBM -> L2 a whole tile ahead of the slot loads
+                    for (int c = 0; c < 2 * kBnNch; ++c) tma_prefetch_l2_2d(&tmRes, c * kBnSlotCols, tile_of(i + 1) * kTcBlockM);
                 for (int c = 0; c < kBnSlotsPerTile && alive; ++c, ++g) {
                     const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
                     if (!bn_wait<PROF>(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58, w_sf)) { alive = false; break; }
@@ -254,69 +258,78 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of a 64-column slot =====================
+        // ===================== epilogue: 2 teams x 4 warps; a warp owns one 32-row slab (TMEM lane quarter) of a whole 64-column slot ==========
+        // Team t takes the slots with running index g = t (mod 2): the two 64-column halves of a conv3 chunk / alternate
+        // conv1 slots are in flight at the same time, and a warp needs no other warp to finish its slab (no named barrier):
+        // TMEM -> +bias (+residual already in the slab) -> ReLU -> bf16 in place -> its own TMA store.
         const int quarter = warp & 3;
-        const int half = (warp - 4) >> 2;
-        const bool issuer = half == 0 && lane == 0;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
+        const int team = (warp - 4) >> 2;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
-        uint32_t g = 0;
-        int pending = -1;                                    // issuer: slot whose TMA store may still be reading smem
+        uint32_t g = static_cast<uint32_t>(team);            // this warp's running slot index (advances by 2)
+        int pending = -1;                                    // lane 0: slot whose TMA store may still be reading smem
         bool alive = true;
-        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_nb = 0, w_bulk = 0, w_ldt = 0;
+        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_bulk = 0, w_ldt = 0;
         const long long e_start = clock64();
 
         auto do_slot = [&](uint32_t tcol, const float* bias, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
             const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
-            uint32_t r[32];
-            tmem_ld32(lane_base + tcol, r);
-            float4 bq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + j);
-            if (!bn_wait<PROF>(sres0 + 8 * slot, use & 1u, p.err_flag, 59, w_sres)) alive = false;
             uint8_t* srow = slots + slot * kBnSlotBytes + slab_off;
-            uint4 rq[4];
-            if (is_conv3) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
-            }
-            if (PROF) { const long long t0 = clock64(); tmem_ld_wait(); w_ldt += clock64() - t0; } else tmem_ld_wait();
-            if (release_bar != 0) {                          // accumulator fully read: hand TMEM back early
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(release_bar);
-            }
+            for (int hf = 0; hf < 2; ++hf) {                 // two 32-column halves of the slab row
+                uint32_t r[32];
+                tmem_ld32(lane_base + tcol + hf * 32, r);
+                float4 bq[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
-                float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
-                float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
-                float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + hf * 32) + j);
+                if (hf == 0 && !bn_wait<PROF>(sres0 + 8 * slot, use & 1u, p.err_flag, 59, w_sres)) alive = false;
+                uint4 rq[4];
                 if (is_conv3) {
-                    v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
-                    v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4));
                 }
-                uint4 o;
-                o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
-                o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
-                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4)) = o;
+                if (PROF) { const long long t0 = clock64(); tmem_ld_wait(); w_ldt += clock64() - t0; } else tmem_ld_wait();
+                if (hf == 1 && release_bar != 0) {           // this warp's part of the accumulator is read: hand TMEM back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(release_bar);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
+                    float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
+                    float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
+                    float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                    if (is_conv3) {
+                        v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
+                        v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+                    }
+                    uint4 o;
+                    o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
+                    o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
+                    *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4)) = o;
+                }
             }
             fence_async_smem();                              // generic-proxy writes -> visible to the TMA store and to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(aready0 + 8 * slot);  // every slot use (conv1 slots too: keeps the barrier's phase == use count)
-            if (PROF) { const long long t0 = clock64(); named_bar_sync(1 + quarter, 64); w_nb += clock64() - t0; }
-            else named_bar_sync(1 + quarter, 64);            // both column halves of this quarter's slab are written
-            if (issuer) {
+            if (lane == 0) {
+                mbar_arrive(aready0 + 8 * slot);             // every slot use (conv1 slots too: keeps the barrier's phase == use count)
                 tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
                 bulk_commit();
-                if (pending >= 0) {                          // the previous store has left shared memory
-                    if (PROF) { const long long t0 = clock64(); bulk_wait_read<1>(); w_bulk += clock64() - t0; } else bulk_wait_read<1>();
-                    mbar_arrive(sfree0 + 8 * pending);
-                }
                 pending = static_cast<int>(slot);
             }
-            ++g;
+            __syncwarp();
+            g += 2;
+        };
+        // Called before the warp waits for its next accumulator: by then the slab store issued a moment ago has read
+        // shared memory, and the slot goes back to the residual prefetcher two slots ahead of its next use.
+        auto release_pending = [&]() {
+            if (lane == 0 && pending >= 0) {
+                if (PROF) { const long long t0 = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - t0; } else bulk_wait_read<0>();
+                mbar_arrive(sfree0 + 8 * pending);
+                pending = -1;
+            }
         };
 
         uint32_t q3 = 0;
@@ -324,25 +337,28 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             const int m = tile_of(i);
             for (int c = 0; c < kBnNch && alive; ++c, ++q3) {
                 const uint32_t s = q3 & 1u;
+                release_pending();
                 if (!bn_wait<PROF>(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60, w_t3f)) { alive = false; break; }
                 tc_fence_after();
-#pragma unroll 1
-                for (int cc = 0; cc < 2 && alive; ++cc)
-                    do_slot(kBnP + s * kBnChunk + cc * kBnSlotCols, p.bias3 + c * kBnChunk + cc * kBnSlotCols, true,
-                            cc == 1 ? t3empty0 + 8 * s : 0u, &tmOut, c * kBnChunk + cc * kBnSlotCols, m * kTcBlockM);
+                do_slot(kBnP + s * kBnChunk + team * kBnSlotCols, p.bias3 + c * kBnChunk + team * kBnSlotCols, true, t3empty0 + 8 * s, &tmOut,
+                        c * kBnChunk + team * kBnSlotCols, m * kTcBlockM);
             }
             if (!alive) break;
+            release_pending();
             if (!bn_wait<PROF>(t1full, static_cast<uint32_t>(i) & 1u, p.err_flag, 61, w_t1f)) { alive = false; break; }
             tc_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < kBnP / kBnSlotCols && alive; ++cc)
-                do_slot(cc * kBnSlotCols, p.bias1 + cc * kBnSlotCols, false, cc == kBnP / kBnSlotCols - 1 ? t1empty : 0u, &tmY1,
-                        cc * kBnSlotCols, m * kTcBlockM);
+            for (int k = 0; k < kBnP / kBnSlotCols / 2 && alive; ++k) {
+                if (k > 0) release_pending();
+                const int cc = 2 * k + team;
+                do_slot(cc * kBnSlotCols, p.bias1 + cc * kBnSlotCols, false, k == kBnP / kBnSlotCols / 2 - 1 ? t1empty : 0u, &tmY1, cc * kBnSlotCols,
+                        m * kTcBlockM);
+            }
         }
-        if (issuer) bulk_wait_read<0>();                     // staged data must stay valid until every store has read it
+        if (lane == 0 && pending >= 0) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
         if (PROF && p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 24;
-            o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = w_nb; o[14] = w_bulk; o[16] = w_ldt;
+            o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = 0; o[14] = w_bulk; o[16] = w_ldt;
         }
         __syncwarp();
     }

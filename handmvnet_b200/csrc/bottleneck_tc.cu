@@ -122,10 +122,10 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(t1full0 + 8 * i, 1);
-            mbar_init(t1empty0 + 8 * i, 8);                 // one arrival per epilogue warp
+            mbar_init(t1empty0 + 8 * i, P == 64 ? 4 : 8);   // one arrival per epilogue warp that reads the conv2 accumulator (P = 64: one chunk, one team)
             mbar_init(t2full0 + 8 * i, 1);
             mbar_init(t2empty0 + 8 * i, 8);
-            mbar_init(y2ready0 + 8 * i, 4);
+            mbar_init(y2ready0 + 8 * i, P == 64 ? 4 : 8);   // every warp that stored a slab of Y2[m]
         }
         for (int i = 0; i < kBtSlots; ++i) {
             mbar_init(cfull0 + 8 * i, 1);
@@ -259,6 +259,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
             bool alive = true;
             long long w_ce = 0;
             for (int i = 0; i < n_i + kBtLag && alive; ++i) {
+                if (p.prefetch && i + 1 >= kBtLag && i + 1 - kBtLag < n_i)      // next segment's residual tile: HBM -> L2 ahead of its slot loads
+                    for (int c = 0; c < Cfg::kNCH * 2; ++c) tma_prefetch_l2_2d(&tmRes, c * kBtChunkCols, tile_of(i + 1 - kBtLag) * kTcBlockM);
                 if (i >= kBtLag) {
                     const int m3 = tile_of(i - kBtLag);
                     for (int c = 0; c < Cfg::kNCH * 2 && alive; ++c, ++g) {
@@ -280,71 +282,78 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of a 64-column chunk =====================
+        // ===================== epilogue: 2 teams x 4 warps; a warp owns one 32-row slab (TMEM lane quarter) of a whole 64-column chunk =========
+        // Every warp walks the chunk sequence; team t processes the chunks whose running index g is t (mod 2), so two
+        // chunks are in flight at a time and a warp needs no other warp to finish its slab (no named barrier):
+        // TMEM -> +bias (+residual already in the slab) -> ReLU -> bf16 in place -> its own TMA store.
         const int quarter = warp & 3;
-        const int half = (warp - 4) >> 2;
-        const bool issuer = half == 0 && lane == 0;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
+        const uint32_t team = static_cast<uint32_t>((warp - 4) >> 2);
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
         uint32_t g = 0;                                      // running chunk counter (slot = g % kBtSlots)
-        int pending = -1;                                    // issuer: slot whose TMA store may still be reading smem
+        int pending = -1;                                    // lane 0: slot whose TMA store may still be reading smem
         bool alive = true;
-        long long w_t2f = 0, w_cf = 0, w_t1f = 0, w_bulk = 0, w_nb = 0;
+        long long w_t2f = 0, w_cf = 0, w_t1f = 0, w_bulk = 0;
 
-        // One 64-column chunk: TMEM -> (+bias, +residual already in the slot) -> ReLU -> bf16 in place -> TMA store.
         auto do_chunk = [&](uint32_t tcol, const float* bias, bool has_res, uint32_t release_bar, const CUtensorMap* tm_out, int col,
                             int row) {
             const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
-            uint32_t r[32];
-            tmem_ld32(lane_base + tcol, r);
-            float4 bq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + j);
-            if (!timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf)) alive = false;
             uint8_t* srow = slots + slot * kBtChunkBytes + slab_off;
-            uint4 rq[4];
-            if (has_res) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4));
-            }
-            tmem_ld_wait();
-            if (release_bar != 0) {                          // accumulator fully read: hand TMEM back early
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(release_bar);
-            }
+            for (int hf = 0; hf < 2; ++hf) {                 // two 32-column halves of the slab row
+                uint32_t r[32];
+                tmem_ld32(lane_base + tcol + hf * 32, r);
+                float4 bq[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
-                float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
-                float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
-                float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + hf * 32) + j);
+                if (hf == 0 && !timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf)) alive = false;
+                uint4 rq[4];
                 if (has_res) {
-                    v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
-                    v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4));
                 }
-                uint4 o;
-                o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
-                o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
-                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(half * 4 + j) ^ (lane & 7)) << 4)) = o;
+                tmem_ld_wait();
+                if (hf == 1 && release_bar != 0) {           // this warp's part of the accumulator is read: hand TMEM back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(release_bar);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 v0 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), make_float2(bq[2 * j].x, bq[2 * j].y));
+                    float2 v1 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), make_float2(bq[2 * j].z, bq[2 * j].w));
+                    float2 v2 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), make_float2(bq[2 * j + 1].x, bq[2 * j + 1].y));
+                    float2 v3 = __fadd2_rn(make_float2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), make_float2(bq[2 * j + 1].z, bq[2 * j + 1].w));
+                    if (has_res) {
+                        v0 = __fadd2_rn(v0, bf16x2_to_f2(rq[j].x)); v1 = __fadd2_rn(v1, bf16x2_to_f2(rq[j].y));
+                        v2 = __fadd2_rn(v2, bf16x2_to_f2(rq[j].z)); v3 = __fadd2_rn(v3, bf16x2_to_f2(rq[j].w));
+                    }
+                    uint4 o;
+                    o.x = cvt_bf16x2(v0.x, v0.y, true); o.y = cvt_bf16x2(v1.x, v1.y, true);
+                    o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
+                    *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4)) = o;
+                }
             }
             fence_async_smem();
-            long long tb = clock64();
-            named_bar_sync(1 + quarter, 64);                 // both column halves of this quarter's slab are written
-            w_nb += clock64() - tb;
-            if (issuer) {
+            __syncwarp();
+            if (lane == 0) {
                 tma_store_2d(tm_out, slots_base + slot * kBtChunkBytes + quarter * (32 * 128), col, row + quarter * 32);
                 bulk_commit();
-                if (pending >= 0) {                          // the previous store has left shared memory: recycle its slot
-                    tb = clock64();
-                    bulk_wait_read<1>();
-                    w_bulk += clock64() - tb;
-                    mbar_arrive(cempty0 + 8 * pending);
-                }
                 pending = static_cast<int>(slot);
             }
-            ++g;
+            __syncwarp();
+        };
+        // Before the warp waits for its next accumulator: the slab store issued a moment ago has read shared memory by
+        // now, and the slot goes back to the residual prefetcher ahead of its next use.
+        auto release_pending = [&]() {
+            if (lane == 0 && pending >= 0) {
+                const long long tb = clock64();
+                bulk_wait_read<0>();
+                w_bulk += clock64() - tb;
+                mbar_arrive(cempty0 + 8 * pending);
+                pending = -1;
+            }
         };
 
         uint32_t q = 0;
@@ -353,25 +362,36 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 const int m3 = tile_of(i - kBtLag);
                 for (int c = 0; c < Cfg::kNCH && alive; ++c, ++q) {
                     const uint32_t s = q & 1u;
+                    release_pending();
                     if (!timed_wait(t2full0 + 8 * s, (q >> 1) & 1u, p.err_flag, 31, w_t2f)) { alive = false; break; }
                     tc_fence_after();
 #pragma unroll 1
-                    for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc)
-                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, p.bias3 + c * kBtN3 + cc * kBtChunkCols, true,
-                                 cc == kBtN3 / kBtChunkCols - 1 ? t2empty0 + 8 * s : 0u, &tmOut, c * kBtN3 + cc * kBtChunkCols,
-                                 m3 * kTcBlockM);
+                    for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc, ++g) {     // two chunks: one per team
+                        if ((g & 1u) != team) continue;
+                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, p.bias3 + c * kBtN3 + cc * kBtChunkCols, true, t2empty0 + 8 * s, &tmOut,
+                                 c * kBtN3 + cc * kBtChunkCols, m3 * kTcBlockM);
+                    }
                 }
             }
             if (i < n_i && alive) {
                 const int m2 = tile_of(i);
                 const uint32_t a = static_cast<uint32_t>(i) % Cfg::kNA, ause = static_cast<uint32_t>(i) / Cfg::kNA;
-                if (!timed_wait(t1full0 + 8 * a, ause & 1u, p.err_flag, 32, w_t1f)) { alive = false; break; }
-                tc_fence_after();
+                constexpr int kN2 = P / kBtChunkCols;        // conv2 output chunks (1, 2 or 4)
+                bool mine = false;
+                for (int cc = 0; cc < kN2; ++cc) mine = mine || (((g + cc) & 1u) == team);
+                if (mine) {
+                    release_pending();
+                    if (!timed_wait(t1full0 + 8 * a, ause & 1u, p.err_flag, 32, w_t1f)) { alive = false; break; }
+                    tc_fence_after();
+                }
 #pragma unroll 1
-                for (int cc = 0; cc < P / kBtChunkCols && alive; ++cc)
-                    do_chunk(a * P + cc * kBtChunkCols, p.bias2 + cc * kBtChunkCols, false, cc == P / kBtChunkCols - 1 ? t1empty0 + 8 * a : 0u,
-                             &tmY2s, cc * kBtChunkCols, m2 * kTcBlockM);
-                if (issuer) {                                // Y2[m2] must be complete in global memory before it is reloaded
+                for (int cc = 0; cc < kN2 && alive; ++cc, ++g) {
+                    if ((g & 1u) != team) continue;
+                    if (cc >= 2) release_pending();
+                    do_chunk(a * P + cc * kBtChunkCols, p.bias2 + cc * kBtChunkCols, false, cc + 2 >= kN2 ? t1empty0 + 8 * a : 0u, &tmY2s,
+                             cc * kBtChunkCols, m2 * kTcBlockM);
+                }
+                if (mine && lane == 0) {                     // Y2[m2] must be complete in global memory before it is reloaded
                     const long long tb = clock64();
                     bulk_wait_all();
                     w_bulk += clock64() - tb;
@@ -382,10 +402,10 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 }
             }
         }
-        if (issuer) bulk_wait_read<0>();                     // staged data must stay valid until every store has read it
+        if (lane == 0 && pending >= 0) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
         if (p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 16;
-            o[7] = w_t2f; o[8] = w_cf; o[9] = w_t1f; o[10] = w_bulk; o[11] = w_nb;
+            o[7] = w_t2f; o[8] = w_cf; o[9] = w_t1f; o[10] = w_bulk; o[11] = 0;
         }
         __syncwarp();
     }

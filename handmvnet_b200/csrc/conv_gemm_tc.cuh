@@ -75,6 +75,7 @@ struct BtParams {
     const float* bias3;                // [4P]  folded BN of conv3
     int* err_flag;
     long long* prof;                   // optional [grid][16] stall counters (HMV_BT_PROF=1), else null
+    int prefetch;                      // 1: L2-prefetch the next tile's residual (HMV_BN_PREFETCH=0 disables)
 };
 struct BtLaunch {
     CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes;
@@ -91,6 +92,7 @@ struct BnParams {
     const float* bias1;                // [256]  folded BN of conv1 (block b+1)
     int* err_flag;
     long long* prof;                   // optional [grid][24] stall counters (HMV_BN_PROF=1), else null
+    int prefetch;                      // 1: L2-prefetch the next tile's HBM-sourced operands (HMV_BN_PREFETCH=0 disables)
 };
 struct BnLaunch {
     CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;

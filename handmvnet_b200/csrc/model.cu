@@ -684,6 +684,10 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
     for (int t = 0; t < 9; ++t) b.p.taps[t] = A.tc.p.taps[t];
     b.p.bias2 = A.bias; b.p.bias3 = B.bias;
     b.p.err_flag = h->err_flag_dev;
+    {
+        const char* e = getenv("HMV_BN_PREFETCH");
+        b.p.prefetch = !(e && e[0] == '0');
+    }
     h->tails.push_back(T);
     return 0;
 }
@@ -708,6 +712,10 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
     b.tmRes = A.tc.tmR; b.tmOut = A.tc.tmC; b.tmY1 = B.tc.tmC;
     b.p.bias3 = A.bias; b.p.bias1 = B.bias;
     b.p.err_flag = h->err_flag_dev;
+    {
+        const char* e = getenv("HMV_BN_PREFETCH");
+        b.p.prefetch = !(e && e[0] == '0');
+    }
     h->seams.push_back(S);
     return 0;
 }
