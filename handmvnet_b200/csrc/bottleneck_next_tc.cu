@@ -73,7 +73,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                        const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 32}
                        const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}  
                        const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
-                       const __grid_constant__ BnParams p) {
+                       const __grid_constant__ BnParams p,
+                       const __grid_constant__ BiasBank bank) {            // conv3 biases [0, 1024), next conv1 biases [1024, 1280)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* slots = smem + kBnStages * kBnStageBytes;
@@ -138,8 +139,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             long long w_e3 = 0, w_e1 = 0;
             for (int i = 0; i < n_i; ++i) {
                 const int m = tile_of(i);
-                if (p.prefetch && i + 1 < n_i)               // next tile's conv2 output: HBM -> L2 a whole tile ahead of its ring loads
-                    for (int kb = 0; kb < kBnKb3; ++kb) tma_prefetch_l2_2d(&tmY2, kb * kTcBlockK, tile_of(i + 1) * kTcBlockM);
                 const bool ok = bn_tile_schedule(
                     [&](int c) {
                         for (int kb = 0; kb < kBnKb3; ++kb) {
@@ -240,8 +239,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             long long w_sf = 0;
             for (int i = 0; i < n_i && alive; ++i) {
                 const int m = tile_of(i);
-                if (p.prefetch && i + 1 < n_i)               // next tile's residual: HBM -> L2 a whole tile ahead of the slot loads
-                    for (int c = 0; c < 2 * kBnNch; ++c) tma_prefetch_l2_2d(&tmRes, c * kBnSlotCols, tile_of(i + 1) * kTcBlockM);
                 for (int c = 0; c < kBnSlotsPerTile && alive; ++c, ++g) {
                     const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
                     if (!bn_wait<PROF>(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58, w_sf)) { alive = false; break; }
@@ -269,19 +266,29 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         uint32_t g = static_cast<uint32_t>(team);            // this warp's running slot index (advances by 2)
         int pending = -1;                                    // lane 0: slot whose TMA store may still be reading smem
         bool alive = true;
-        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_bulk = 0, w_ldt = 0;
+        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_bulk = 0, w_ldt = 0, w_math = 0, w_fence = 0, w_issue = 0, w_head = 0;
         const long long e_start = clock64();
 
-        auto do_slot = [&](uint32_t tcol, const float* bias, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
+        // The slab store issued a while ago has read shared memory: the slot may be overwritten (once its MMAs retired too).
+        auto release_pending = [&]() {
+            if (lane == 0 && pending >= 0) {
+                if (PROF) { const long long t0 = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - t0; } else bulk_wait_read<0>();
+                mbar_arrive(sfree0 + 8 * pending);
+                pending = -1;
+            }
+        };
+
+        auto do_slot = [&](uint32_t tcol, int bias_off, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
             const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
             uint8_t* srow = slots + slot * kBnSlotBytes + slab_off;
+            long long tp = PROF ? clock64() : 0;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {                 // two 32-column halves of the slab row
                 uint32_t r[32];
                 tmem_ld32(lane_base + tcol + hf * 32, r);
                 float4 bq[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + hf * 32) + j);
+                for (int j = 0; j < 8; ++j) bq[j] = *reinterpret_cast<const float4*>(&bank.v[bias_off + hf * 32 + 4 * j]);   // constant cache
                 if (hf == 0 && !bn_wait<PROF>(sres0 + 8 * slot, use & 1u, p.err_flag, 59, w_sres)) alive = false;
                 uint4 rq[4];
                 if (is_conv3) {
@@ -289,7 +296,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     for (int j = 0; j < 4; ++j)
                         rq[j] = *reinterpret_cast<const uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4));
                 }
-                if (PROF) { const long long t0 = clock64(); tmem_ld_wait(); w_ldt += clock64() - t0; } else tmem_ld_wait();
+                if (PROF) { const long long t0 = clock64(); w_head += t0 - tp; tmem_ld_wait(); tp = clock64(); w_ldt += tp - t0; } else tmem_ld_wait();
                 if (hf == 1 && release_bar != 0) {           // this warp's part of the accumulator is read: hand TMEM back early
                     tc_fence_before();
                     __syncwarp();
@@ -310,9 +317,11 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     o.z = cvt_bf16x2(v2.x, v2.y, true); o.w = cvt_bf16x2(v3.x, v3.y, true);
                     *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(hf * 4 + j) ^ (lane & 7)) << 4)) = o;
                 }
+                if (PROF) { const long long t0 = clock64(); w_math += t0 - tp; tp = t0; }
             }
             fence_async_smem();                              // generic-proxy writes -> visible to the TMA store and to the tensor core
             __syncwarp();
+            if (PROF) { const long long t0 = clock64(); w_fence += t0 - tp; tp = t0; }
             if (lane == 0) {
                 mbar_arrive(aready0 + 8 * slot);             // every slot use (conv1 slots too: keeps the barrier's phase == use count)
                 tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
@@ -320,16 +329,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                 pending = static_cast<int>(slot);
             }
             __syncwarp();
+            if (PROF) { w_issue += clock64() - tp; }
             g += 2;
-        };
-        // Called before the warp waits for its next accumulator: by then the slab store issued a moment ago has read
-        // shared memory, and the slot goes back to the residual prefetcher two slots ahead of its next use.
-        auto release_pending = [&]() {
-            if (lane == 0 && pending >= 0) {
-                if (PROF) { const long long t0 = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - t0; } else bulk_wait_read<0>();
-                mbar_arrive(sfree0 + 8 * pending);
-                pending = -1;
-            }
         };
 
         uint32_t q3 = 0;
@@ -337,10 +338,10 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             const int m = tile_of(i);
             for (int c = 0; c < kBnNch && alive; ++c, ++q3) {
                 const uint32_t s = q3 & 1u;
-                release_pending();
+                release_pending();                           // the slot goes back to the residual prefetcher ahead of its next use
                 if (!bn_wait<PROF>(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60, w_t3f)) { alive = false; break; }
                 tc_fence_after();
-                do_slot(kBnP + s * kBnChunk + team * kBnSlotCols, p.bias3 + c * kBnChunk + team * kBnSlotCols, true, t3empty0 + 8 * s, &tmOut,
+                do_slot(kBnP + s * kBnChunk + team * kBnSlotCols, c * kBnChunk + team * kBnSlotCols, true, t3empty0 + 8 * s, &tmOut,
                         c * kBnChunk + team * kBnSlotCols, m * kTcBlockM);
             }
             if (!alive) break;
@@ -351,7 +352,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             for (int k = 0; k < kBnP / kBnSlotCols / 2 && alive; ++k) {
                 if (k > 0) release_pending();
                 const int cc = 2 * k + team;
-                do_slot(cc * kBnSlotCols, p.bias1 + cc * kBnSlotCols, false, k == kBnP / kBnSlotCols / 2 - 1 ? t1empty : 0u, &tmY1, cc * kBnSlotCols,
+                do_slot(cc * kBnSlotCols, kBnBias1Off + cc * kBnSlotCols, false, k == kBnP / kBnSlotCols / 2 - 1 ? t1empty : 0u, &tmY1, cc * kBnSlotCols,
                         m * kTcBlockM);
             }
         }
@@ -359,6 +360,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         if (PROF && p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 24;
             o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = 0; o[14] = w_bulk; o[16] = w_ldt;
+            o[17] = w_head; o[18] = w_math; o[19] = w_fence; o[20] = w_issue;
         }
         __syncwarp();
     }
@@ -384,10 +386,10 @@ int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
     if (l.p.prof)
         HMV_CUDA(launch_kernel(bottleneck_next_kernel<true>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
-                               l.tmW1, l.tmY1, l.p));
+                               l.tmW1, l.tmY1, l.p, l.bank));
     else
         HMV_CUDA(launch_kernel(bottleneck_next_kernel<false>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
-                               l.tmW1, l.tmY1, l.p));
+                               l.tmW1, l.tmY1, l.p, l.bank));
     return 0;
 }
 

@@ -91,7 +91,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                        const __grid_constant__ CUtensorMap tmW3,   // [4P, P] box {64, 128}
                        const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 4P], store box {64, 32}
                        const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 4P], load box {64, 128}
-                       const __grid_constant__ BtParams p) {
+                       const __grid_constant__ BtParams p,
+                       const __grid_constant__ BiasBank bank) {            // conv2 biases [0, P), conv3 biases [256, 256 + 4P)
     using Cfg = BtCfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -295,7 +296,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         bool alive = true;
         long long w_t2f = 0, w_cf = 0, w_t1f = 0, w_bulk = 0;
 
-        auto do_chunk = [&](uint32_t tcol, const float* bias, bool has_res, uint32_t release_bar, const CUtensorMap* tm_out, int col,
+        auto do_chunk = [&](uint32_t tcol, int bias_off, bool has_res, uint32_t release_bar, const CUtensorMap* tm_out, int col,
                             int row) {
             const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
             uint8_t* srow = slots + slot * kBtChunkBytes + slab_off;
@@ -305,7 +306,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 tmem_ld32(lane_base + tcol + hf * 32, r);
                 float4 bq[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + hf * 32) + j);
+                for (int j = 0; j < 8; ++j) bq[j] = *reinterpret_cast<const float4*>(&bank.v[bias_off + hf * 32 + 4 * j]);   // constant cache
                 if (hf == 0 && !timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf)) alive = false;
                 uint4 rq[4];
                 if (has_res) {
@@ -368,7 +369,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 #pragma unroll 1
                     for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc, ++g) {     // two chunks: one per team
                         if ((g & 1u) != team) continue;
-                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, p.bias3 + c * kBtN3 + cc * kBtChunkCols, true, t2empty0 + 8 * s, &tmOut,
+                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, kBtBias3Off + c * kBtN3 + cc * kBtChunkCols, true, t2empty0 + 8 * s, &tmOut,
                                  c * kBtN3 + cc * kBtChunkCols, m3 * kTcBlockM);
                     }
                 }
@@ -388,7 +389,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 for (int cc = 0; cc < kN2 && alive; ++cc, ++g) {
                     if ((g & 1u) != team) continue;
                     if (cc >= 2) release_pending();
-                    do_chunk(a * P + cc * kBtChunkCols, p.bias2 + cc * kBtChunkCols, false, cc + 2 >= kN2 ? t1empty0 + 8 * a : 0u, &tmY2s,
+                    do_chunk(a * P + cc * kBtChunkCols, cc * kBtChunkCols, false, cc + 2 >= kN2 ? t1empty0 + 8 * a : 0u, &tmY2s,
                              cc * kBtChunkCols, m2 * kTcBlockM);
                 }
                 if (mine && lane == 0) {                     // Y2[m2] must be complete in global memory before it is reloaded
@@ -422,7 +423,7 @@ template <int P>
 int bt_launch_p(const BtLaunch& l, int num_sms, cudaStream_t stream) {
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
     HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
-                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.p));
+                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.p, l.bank));
     return 0;
 }
 

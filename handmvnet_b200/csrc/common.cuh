@@ -109,6 +109,14 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Folded-BN biases of a launch, passed BY VALUE as a __grid_constant__ kernel parameter: the epilogue warps then read them
+// through the constant cache (one broadcast LDC per value).  With ~227 KB of shared memory carved out per CTA the L1
+// is almost gone, and the former `__ldg(bias + col)` loads went to L2 on every 64-column chunk: ~850 cycles of
+// exposed latency per chunk per warp, the largest single cost of the epilogues (measured with HMV_BN_PROF=1,
+// profiles/r02/README.md).  1280 floats = conv3 (1024) + the next conv1 (256) of the fused layer3 seam.
+constexpr int kBiasBankFloats = 1280;
+struct BiasBank { float v[kBiasBankFloats]; };
+
 // Epilogue description shared by the tensor-core and the fp32 implicit-GEMM kernels.
 enum OutMode { OUT_BF16_ROWMAJOR = 0, OUT_F32_ROWMAJOR = 1, OUT_F32_NCHW = 2 };
 enum ResMode { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };

@@ -11,10 +11,11 @@ namespace hmv {
 // ------------------------------------------------------------------------------------------------
 // epilogue: 16 consecutive output columns of one row
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_16(const Epilogue& ep, float (&v)[16], int row, int col0) {
+__device__ __forceinline__ void epilogue_16(const Epilogue& ep, const BiasBank& bank, bool bias_in_params, float (&v)[16], int row, int col0) {
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+        const float4 b = bias_in_params ? *reinterpret_cast<const float4*>(&bank.v[col0 + i])
+                                        : __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
     if (ep.res_mode != RES_NONE) {
@@ -100,7 +101,7 @@ template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                    const __grid_constant__ TcParams p) {
+                    const __grid_constant__ TcParams p, const __grid_constant__ BiasBank bank) {
     using Cfg = TcCfg<BN, MODE>;
     static_assert(CL == 1 || (CL == 2 && BN % 16 == 0), "cluster width");
     const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
@@ -272,11 +273,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-                if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c);
+                if (row_ok) epilogue_16(p.ep, bank, p.bias_in_params != 0, v, row, n_tile * BN + c);
                 if (c + 16 < BN) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
-                    if (row_ok) epilogue_16(p.ep, v, row, n_tile * BN + c + 16);
+                    if (row_ok) epilogue_16(p.ep, bank, p.bias_in_params != 0, v, row, n_tile * BN + c + 16);
                 }
             }
             tc_fence_before();
@@ -315,7 +316,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int col0 = n_tile * BN + c * kChunkCols + half * 32;
                 float4 bq[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + j);
+                for (int j = 0; j < 8; ++j)
+                    bq[j] = p.bias_in_params ? *reinterpret_cast<const float4*>(&bank.v[col0 + 4 * j])
+                                             : __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + j);
                 const uint32_t slab_off = Cfg::kStages * Cfg::kStageBytes + quarter * (32 * 128) + lane * 128;
                 uint4 rq[4];
                 if (has_res) {
@@ -492,14 +495,14 @@ static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
             const int items = ((l.p.num_m_tiles + 1) / 2) * l.p.num_n_tiles;
             const int clusters = items < max_clusters ? items : max_clusters;
             HMV_CUDA(launch_kernel_cluster(conv_gemm_tc_kernel<BN, MODE, 2>, dim3(2 * clusters), dim3(kTcThreads), 2,
-                                           TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB, l.tmC, l.tmR, l.p));
+                                           TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB, l.tmC, l.tmR, l.p, l.bank));
             return 0;
         }
     }
     const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
     HMV_CUDA(launch_kernel(conv_gemm_tc_kernel<BN, MODE, 1>, dim3(grid), dim3(kTcThreads), TcCfg<BN, MODE>::kSmemBytes, stream, l.tmA, l.tmB,
-                           l.tmC, l.tmR, l.p));
+                           l.tmC, l.tmR, l.p, l.bank));
     return 0;
 }
 

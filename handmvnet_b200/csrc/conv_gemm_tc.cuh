@@ -38,6 +38,7 @@ struct TcParams {
     TcTap taps[kTcMaxTaps];
     Epilogue ep;
     int* err_flag;                     // set to non-zero on an mbarrier timeout
+    int bias_in_params;                // 1: biases come from the BiasBank kernel parameter (N_alloc <= kBiasBankFloats), 0: from ep.bias
 };
 
 // Epilogue variants.  DIRECT: registers -> global (fp32 / NCHW / remapped-residual outputs).
@@ -48,6 +49,7 @@ struct TcParams {
 enum TcMode { TC_DIRECT = 0, TC_STORE = 1, TC_STORE_DEEP = 2, TC_STORE_RES = 3 };
 
 struct TcLaunch {                      // everything needed to enqueue one layer
+    BiasBank bank;                     // [N_alloc] biases when p.bias_in_params
     CUtensorMap tmA, tmB;
     CUtensorMap tmC, tmR;              // output / residual maps (TC_STORE* only)
     TcParams p;
@@ -71,13 +73,13 @@ struct BtParams {
     int num_m_tiles;
     int tpi, hbox, cblks;              // conv2 tile geometry (as TcParams) ; cblks = P / 64
     TcTap taps[kTcMaxTaps];
-    const float* bias2;                // [P]   folded BN of conv2
-    const float* bias3;                // [4P]  folded BN of conv3
     int* err_flag;
     long long* prof;                   // optional [grid][16] stall counters (HMV_BT_PROF=1), else null
     int prefetch;                      // 1: L2-prefetch the next tile's residual (HMV_BN_PREFETCH=0 disables)
 };
+constexpr int kBtBias3Off = 256;       // BiasBank layout of the fused tail: conv2 biases at [0, P), conv3 biases at [256, 256 + 4P)
 struct BtLaunch {
+    BiasBank bank;
     CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes;
     BtParams p;
     int planes;                        // P in {64, 128, 256}
@@ -88,13 +90,12 @@ int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream);
 // ---- fused bottleneck seam (bottleneck_next_tc.cu): conv3 + residual + ReLU of block b -> conv1 + ReLU of block b+1 (P = 256) ----
 struct BnParams {
     int num_m_tiles;
-    const float* bias3;                // [1024] folded BN of conv3 (block b)
-    const float* bias1;                // [256]  folded BN of conv1 (block b+1)
     int* err_flag;
     long long* prof;                   // optional [grid][24] stall counters (HMV_BN_PROF=1), else null
-    int prefetch;                      // 1: L2-prefetch the next tile's HBM-sourced operands (HMV_BN_PREFETCH=0 disables)
 };
+constexpr int kBnBias1Off = 1024;      // BiasBank layout of the fused seam: conv3 biases at [0, 1024), next conv1 biases at [1024, 1280)
 struct BnLaunch {
+    BiasBank bank;
     CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;
     BnParams p;
 };

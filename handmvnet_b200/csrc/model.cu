@@ -82,6 +82,7 @@ struct Layer {
     int max_units = 0;                            // images (convs) or rows (linears) the maps cover
     void* w = nullptr;                            // device [n_alloc, K] (bf16 | fp32)
     float* bias = nullptr;                        // device [n_alloc]
+    std::vector<float> bias_host;                 // the same values on the host (BiasBank kernel parameters)
     const void* in = nullptr;
     Epilogue ep{};
     TcLaunch tc{};
@@ -342,6 +343,7 @@ static int finish_layer(hmv_handle* h, Layer& L, const std::vector<float>& wmat,
     }
     if (upload_weights(h, &L.w, wp)) return 1;
     if (upload_f32(h, &L.bias, bp)) return 1;
+    L.bias_host = bp;
     L.ep.bias = L.bias;
     L.ep.N = L.cout;
     HMV_CHECK(!h->bf16 || L.ep.out_mode == OUT_F32_NCHW || L.ep.ldc >= L.n_alloc,
@@ -352,6 +354,9 @@ static int finish_layer(hmv_handle* h, Layer& L, const std::vector<float>& wmat,
 static int build_tc(hmv_handle* h, Layer& L) {
     TcLaunch& t = L.tc;
     memset(&t.p, 0, sizeof(t.p));
+    memset(&t.bank, 0, sizeof(t.bank));
+    t.p.bias_in_params = L.n_alloc <= kBiasBankFloats ? 1 : 0;      // (the 3072-wide QKV projection keeps the pointer path)
+    if (t.p.bias_in_params) memcpy(t.bank.v, L.bias_host.data(), sizeof(float) * L.n_alloc);
     t.bn = L.bn;
     t.p.num_n_tiles = L.n_alloc / L.bn;
     t.p.err_flag = h->err_flag_dev;
@@ -539,8 +544,9 @@ static int run_seam(hmv_handle* h, int seam, int units, cudaStream_t s) {
             const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
             for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) a[k] += static_cast<double>(host[c * 24 + k]) / grid;
             fprintf(stderr, "[bn_prof] %s tiles/cta %.1f | mma total %.0f: t3empty %.0f full3 %.0f t1empty %.0f aready %.0f full1 %.0f | prod: empty3 %.0f empty1 %.0f | "
-                    "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f namedbar %.0f bulk %.0f tmem_ld %.0f (cycles, mean over CTAs)\n",
-                    S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16]);
+                    "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f namedbar %.0f bulk %.0f tmem_ld %.0f | per-slot phases (incl. the waits above): head %.0f ldwait %.0f math+sts %.0f fence %.0f issue %.0f (cycles, mean over CTAs)\n",
+                    S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16],
+                    a[17], a[16], a[18], a[19], a[20]);
             ++printed;
         }
         return rc;
@@ -682,11 +688,13 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
     b.p.tpi = A.tc.p.tpi; b.p.hbox = A.tc.p.hbox; b.p.cblks = A.tc.p.cblks;
     HMV_CHECK(A.tc.p.num_taps == 9 && b.p.cblks * 64 == P, "fused bottleneck tail: conv2 must be a 3x3 with P input channels");
     for (int t = 0; t < 9; ++t) b.p.taps[t] = A.tc.p.taps[t];
-    b.p.bias2 = A.bias; b.p.bias3 = B.bias;
+    memset(&b.bank, 0, sizeof(b.bank));
+    memcpy(b.bank.v, A.bias_host.data(), sizeof(float) * P);
+    memcpy(b.bank.v + kBtBias3Off, B.bias_host.data(), sizeof(float) * 4 * P);
     b.p.err_flag = h->err_flag_dev;
     {
-        const char* e = getenv("HMV_BN_PREFETCH");
-        b.p.prefetch = !(e && e[0] == '0');
+        const char* e = getenv("HMV_BN_PREFETCH");         // measured neutral (P = 64) to harmful (P = 128): off
+        b.p.prefetch = e && e[0] == '1';
     }
     h->tails.push_back(T);
     return 0;
@@ -710,12 +718,10 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
         return 1;
     }
     b.tmRes = A.tc.tmR; b.tmOut = A.tc.tmC; b.tmY1 = B.tc.tmC;
-    b.p.bias3 = A.bias; b.p.bias1 = B.bias;
+    memset(&b.bank, 0, sizeof(b.bank));
+    memcpy(b.bank.v, A.bias_host.data(), sizeof(float) * 1024);
+    memcpy(b.bank.v + kBnBias1Off, B.bias_host.data(), sizeof(float) * 256);
     b.p.err_flag = h->err_flag_dev;
-    {
-        const char* e = getenv("HMV_BN_PREFETCH");
-        b.p.prefetch = !(e && e[0] == '0');
-    }
     h->seams.push_back(S);
     return 0;
 }
