@@ -10,7 +10,7 @@ Runs only in the build container (needs /root/reference).  For every case it
      stage tensor.
 The fixtures are what pins `oracle/handmvnet_oracle.py` (tests/test_oracle_golden.py).
 
-usage:  python oracle/gen_golden.py
+usage:  python oracle/gen_golden.py [case ...]
 """
 import os
 import sys
@@ -29,6 +29,8 @@ CASES = [
     ("ho3d_v5_plain",  "HO3D_HandMvNet",           2,     1,      77,     False),
     ("dexycb_v8_rand", "DexYCB_HandMvNet",         1,     2,      5,      True),
     ("ho3d_v5_wo_cam", "HO3D_HandMvNet_wo_cam",    1,     3,      9,      True),
+    ("ho3d_v5_hr",     "HO3D_HandMvNet_HR",        1,     4,      11,     True),      # HRNet-w40, 4 feature levels, d_model 312
+    ("mvhand_v4_hr_wo_cam", "MVHand_HandMvNet_HR_wo_cam", 1, 5,   13,     False),     # HRNet-w40, 4 views, no "crop"
 ]
 
 
@@ -48,10 +50,13 @@ def main():
     torch.set_num_threads(os.cpu_count())
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])                      # optional: names of the cases to (re)generate
     for name, yaml_name, batch, seed_w, seed_x, rnd in CASES:
+        if only and name not in only:
+            continue
         cfg = ref_shim.load_cfg(yaml_name)
         model = ref_shim.build_reference(cfg)
-        ocfg = O.release_config(cfg["model"]["num_views"], "crop" in cfg["model"]["pos_enc"])
+        ocfg = O.release_config(cfg["model"]["num_views"], "crop" in cfg["model"]["pos_enc"], cfg["model"]["backbone"])
         sd = O.make_state_dict(ocfg, seed=seed_w, randomize_norm=rnd)
         ref_keys = list(model.state_dict().keys())
         assert ref_keys == list(sd.keys()), "state_dict key order/names differ from the reference"
@@ -66,13 +71,25 @@ def main():
                 stage[key] = out.detach().clone()
             return hook
 
-        hooks = [
-            model.backbone.maxpool.register_forward_hook(keep("stem")),
-            model.backbone.layer1.register_forward_hook(keep("layer1")),
-            model.backbone.layer2.register_forward_hook(keep("layer2")),
-            model.backbone.register_forward_hook(keep("backbone_out")),
+        hr = cfg["model"]["backbone"] == "hrnet"
+        if hr:
+            def keep_levels(_m, _inp, out):
+                for l, t in enumerate(out):
+                    stage[f"level{l}"] = t.detach().clone()
+            hooks = [model.backbone.layer1.register_forward_hook(keep("hr.layer1")),
+                     model.backbone.stage2.register_forward_hook(lambda _m, _i, out: stage.__setitem__("hr.stage2.0.out1", out[1].detach().clone())),
+                     model.backbone.stage3.register_forward_hook(lambda _m, _i, out: stage.__setitem__("hr.stage3.3.out2", out[2].detach().clone())),
+                     model.backbone.register_forward_hook(keep_levels)]
+        else:
+            hooks = [
+                model.backbone.maxpool.register_forward_hook(keep("stem")),
+                model.backbone.layer1.register_forward_hook(keep("layer1")),
+                model.backbone.layer2.register_forward_hook(keep("layer2")),
+                model.backbone.register_forward_hook(keep("backbone_out")),
+                model.sample_nets[0].register_forward_hook(keep("sampled")),
+            ]
+        hooks += [
             model.pose_net.register_forward_hook(keep("heatmap")),
-            model.sample_nets[0].register_forward_hook(keep("sampled")),
             model.joints_late_fusion.register_forward_pre_hook(
                 lambda _m, inp: stage.__setitem__("tokens", inp[0].detach().clone())),
             model.joints_decoder.register_forward_hook(keep("joints_cam")),
@@ -92,6 +109,7 @@ def main():
             "meta_seed_x": np.int64(seed_x), "meta_randomize_norm": np.bool_(rnd),
             "meta_num_views": np.int64(cfg["model"]["num_views"]),
             "meta_crop": np.bool_("crop" in cfg["model"]["pos_enc"]),
+            "meta_backbone": np.array(cfg["model"]["backbone"]),
             "meta_torch": np.array(torch.__version__),
             "out_joints_cam": out["joints_cam"].numpy(),
             "out_joints_crop_img": out["joints_crop_img"].numpy(),
@@ -107,7 +125,7 @@ def main():
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); "
               f"mean|joints_cam|={out['joints_cam'].abs().mean():.4e} "
               f"mean|heatmap|={out['heatmap'].abs().mean():.4f} "
-              f"backbone std={stage['backbone_out'].std():.3f}")
+              f"backbone std={stage['level0' if hr else 'backbone_out'].std():.3f}")
 
 
 if __name__ == "__main__":

@@ -33,6 +33,9 @@ HAND_EDGES = [(0, 1), (1, 2), (2, 3), (3, 4),
               (0, 17), (17, 18), (18, 19), (19, 20)]
 
 NUM_JOINTS = 21
+# reference backbones/hrnet.py:427-495: branch widths; stage2..4 = (modules, branches), 4 BasicBlocks per branch
+HR_CHANNELS = {"w40": (40, 80, 160, 320), "w64": (64, 128, 256, 512)}
+HR_STAGES = ((1, 2), (4, 3), (3, 4))
 BN_EPS = 1e-5
 LN_EPS = 1e-5
 LAYER_BLOCKS = (3, 4, 6)           # resnet.py:352 layers=[3,4,6,3], variant "paper" drops layer4
@@ -43,10 +46,21 @@ LAYER_STRIDES = (1, 2, 1)          # resnet.py:164-177 (paper variant: layer3 st
 # ----------------------------------------------------------------------------
 # configuration
 # ----------------------------------------------------------------------------
-def release_config(num_views: int = 5, crop: bool = True) -> dict:
-    """The fields of configs/release/{HO3D,DexYCB}_HandMvNet[_wo_cam].yaml that the
-    forward path reads (reference src/config.py:35-51 derives num_views)."""
+def release_config(num_views: int = 5, crop: bool = True, backbone: str = "resnet") -> dict:
+    """The fields of configs/release/{HO3D,DexYCB,MVHand}_HandMvNet[_HR][_wo_cam].yaml that the
+    forward path reads (reference src/config.py:35-51 derives num_views).  backbone="hrnet" gives the
+    `*_HR*.yaml` family (HRNet-w40, four feature levels)."""
     pos_enc = ["pos2d", "crop", "sin"] if crop else ["pos2d", "sin"]
+    if backbone == "hrnet":
+        return {
+            "data": {"name": "ho3d", "batch_size": 16, "heatmap_size": 32, "image_size": 256},
+            "model": {"selected_views": list(range(num_views)), "num_views": num_views,
+                      "fusion": "cross_attn", "fusion_layers": 5, "pos_enc": pos_enc,
+                      "use_gcn": True, "backbone": "hrnet", "backbone_type": "w40",
+                      "backbone_pretrained_path": "", "backbone_channels": list(HR_CHANNELS["w40"]),
+                      "backbone_pretrained": False},
+            "train": {"debug": False, "root_relative": True, "device": "cpu"},
+        }
     return {
         "data": {"name": "ho3d", "batch_size": 16, "heatmap_size": 32, "image_size": 256},
         "model": {"selected_views": list(range(num_views)), "num_views": num_views,
@@ -89,6 +103,8 @@ def _state_dict_spec(cfg: dict):
         spec.append((name + ".running_var", (c,), "bn_var"))
         spec.append((name + ".num_batches_tracked", (), "count"))
 
+    if cfg["model"].get("backbone", "resnet") == "hrnet":
+        return _hrnet_state_dict_spec(cfg, spec, conv, bn)
     conv("backbone.conv1", 64, 3, 7, False, "kaiming_out")
     bn("backbone.bn1", 64)
     inplanes = 64
@@ -106,6 +122,66 @@ def _state_dict_spec(cfg: dict):
     conv("pose_net.0", 512, c, 1, True, "default_conv"); bn("pose_net.1", 512)
     conv("pose_net.3", NUM_JOINTS, 512, 1, True, "default_conv")
     conv("sample_nets.0.conv.0", c // 2, c, 1, True, "default_conv"); bn("sample_nets.0.conv.1", c // 2)
+    _head_spec(cfg, spec)
+    return spec
+
+
+def _hrnet_state_dict_spec(cfg, spec, conv, bn):
+    """Keys of the `*_HR*` models in the reference's registration order (backbones/hrnet.py:241-276 HighResolutionNet,
+    :97-120 HighResolutionModule, :26-36 BasicBlock, :61-72 Bottleneck; handmvnet.py:41-56 pose_net, :97 sample_nets);
+    1941 keys for w40, verified key-for-key by gen_golden.py.  Every HRNet conv is bias-free and kaiming(fan_out)
+    initialised (hrnet.py:412-418)."""
+    ch = tuple(cfg["model"]["backbone_channels"])
+    conv("backbone.conv1", 64, 3, 3, False, "kaiming_out"); bn("backbone.bn1", 64)
+    conv("backbone.conv2", 64, 64, 3, False, "kaiming_out"); bn("backbone.bn2", 64)
+    inpl = 64
+    for b in range(4):                                   # stage1: 4 Bottlenecks, 64 planes
+        p = f"backbone.layer1.{b}"
+        conv(p + ".conv1", 64, inpl, 1, False, "kaiming_out"); bn(p + ".bn1", 64)
+        conv(p + ".conv2", 64, 64, 3, False, "kaiming_out"); bn(p + ".bn2", 64)
+        conv(p + ".conv3", 256, 64, 1, False, "kaiming_out"); bn(p + ".bn3", 256)
+        if b == 0:
+            conv(p + ".downsample.0", 256, inpl, 1, False, "kaiming_out"); bn(p + ".downsample.1", 256)
+        inpl = 256
+    pre = [256]
+    for si, (nmod, nbr) in enumerate(HR_STAGES, start=2):
+        cur = list(ch[:nbr])
+        t = f"backbone.transition{si - 1}"
+        for i in range(nbr):                             # hrnet.py:318-345
+            if i < len(pre):
+                if cur[i] != pre[i]:
+                    conv(f"{t}.{i}.0", cur[i], pre[i], 3, False, "kaiming_out"); bn(f"{t}.{i}.1", cur[i])
+            else:
+                for j in range(i + 1 - len(pre)):
+                    outc = cur[i] if j == i - len(pre) else pre[-1]
+                    conv(f"{t}.{i}.{j}.0", outc, pre[-1], 3, False, "kaiming_out"); bn(f"{t}.{i}.{j}.1", outc)
+        for m in range(nmod):
+            sname = f"backbone.stage{si}.{m}"
+            for i in range(nbr):
+                for blk in range(4):
+                    q = f"{sname}.branches.{i}.{blk}"
+                    conv(q + ".conv1", cur[i], cur[i], 3, False, "kaiming_out"); bn(q + ".bn1", cur[i])
+                    conv(q + ".conv2", cur[i], cur[i], 3, False, "kaiming_out"); bn(q + ".bn2", cur[i])
+            for i in range(nbr):                         # hrnet.py:177-211
+                for j in range(nbr):
+                    f = f"{sname}.fuse_layers.{i}.{j}"
+                    if j > i:
+                        conv(f + ".0", cur[i], cur[j], 1, False, "kaiming_out"); bn(f + ".1", cur[i])
+                    elif j < i:
+                        for k in range(i - j):
+                            outc = cur[i] if k == i - j - 1 else cur[j]
+                            conv(f"{f}.{k}.0", outc, cur[j], 3, False, "kaiming_out"); bn(f"{f}.{k}.1", outc)
+        pre = cur
+    spec.append(("pose_net.weight", (NUM_JOINTS, ch[0], 3, 3), "default_conv"))
+    spec.append(("pose_net.bias", (NUM_JOINTS,), "bias_fanin:%d" % (ch[0] * 9)))
+    for l, c in enumerate(ch):
+        conv(f"sample_nets.{l}.conv.0", c // 2, c, 1, True, "default_conv"); bn(f"sample_nets.{l}.conv.1", c // 2)
+    _head_spec(cfg, spec)
+    return spec
+
+
+def _head_spec(cfg, spec):
+    """fusion transformer + graph head keys (shared by both backbones)."""
     d = feat_dim_of(cfg)
     for i in range(cfg["model"].get("fusion_layers", 5)):
         p = f"joints_late_fusion.attn_fusion.{i}"
@@ -123,7 +199,6 @@ def _state_dict_spec(cfg: dict):
     for i, (cin, cout) in enumerate(((d, 256), (256, 64), (64, 3)), 1):
         spec.append((f"joints_decoder.joints_gcn{i}.weight", (3, 1, cin, cout), "xavier_cheb"))
         spec.append((f"joints_decoder.joints_gcn{i}.bias", (1, 1, cout), "cheb_bias"))
-    return spec
 
 
 def make_state_dict(cfg: dict, seed: int = 0, randomize_norm: bool = True) -> "OrderedDict[str, torch.Tensor]":
@@ -232,6 +307,91 @@ def backbone(sd, x, taps=None, per_layer=False):
     return x
 
 
+def _conv_bn(sd, conv, bn, x, stride=1, relu=True):
+    """bias-free conv (kernel from the weight shape, "same" padding) + eval BatchNorm (+ ReLU)."""
+    w = sd[conv + ".weight"]
+    y = _bn(sd, bn, F.conv2d(x, w, stride=stride, padding=w.shape[-1] // 2))
+    return F.relu(y) if relu else y
+
+
+def basic_block(sd, p, x):
+    """reference hrnet.py:38-55 (BasicBlock.forward, no downsample in HRNet branches)."""
+    out = _conv_bn(sd, p + ".conv1", p + ".bn1", x)
+    out = _conv_bn(sd, p + ".conv2", p + ".bn2", out, relu=False)
+    return F.relu(out + x)
+
+
+def hr_module(sd, p, xs, taps=None, key=None):
+    """reference hrnet.py:216-233 (HighResolutionModule.forward): 4 BasicBlocks per branch, then every output branch i is
+    relu(sum_j f_ij(x_j)) with f_ij = identity (j == i), 1x1 conv + BN + nearest upsample (j > i), or a chain of
+    3x3 stride-2 conv + BN (+ ReLU except the last) (j < i) - summed in the reference's order."""
+    nbr = len(xs)
+    xs = list(xs)
+    for i in range(nbr):
+        for blk in range(4):
+            xs[i] = basic_block(sd, f"{p}.branches.{i}.{blk}", xs[i])
+        if taps is not None:
+            taps[f"{key}.branch{i}"] = xs[i]
+    outs = []
+    for i in range(nbr):
+        y = None
+        for j in range(nbr):
+            f = f"{p}.fuse_layers.{i}.{j}"
+            if j == i:
+                t = xs[j]
+            elif j > i:
+                t = _conv_bn(sd, f + ".0", f + ".1", xs[j], relu=False)
+                t = F.interpolate(t, scale_factor=2 ** (j - i), mode="nearest")
+            else:
+                t = xs[j]
+                for k in range(i - j):
+                    t = _conv_bn(sd, f"{f}.{k}.0", f"{f}.{k}.1", t, stride=2, relu=k < i - j - 1)
+            y = t if y is None else y + t
+        outs.append(F.relu(y))
+        if taps is not None:
+            taps[f"{key}.out{i}"] = outs[-1]
+    return outs
+
+
+def hrnet_backbone(sd, x, taps=None):
+    """reference hrnet.py:377-409 (HighResolutionNet.forward) for w40 / w64: two stride-2 3x3 stem convs, 4 Bottlenecks,
+    then stages 2-4 with their transitions -> [N,C0,64,64], [N,C1,32,32], [N,C2,16,16], [N,C3,8,8]."""
+    x = _conv_bn(sd, "backbone.conv1", "backbone.bn1", x, stride=2)
+    if taps is not None:
+        taps["hr.conv1"] = x
+    x = _conv_bn(sd, "backbone.conv2", "backbone.bn2", x, stride=2)
+    if taps is not None:
+        taps["hr.conv2"] = x
+    for b in range(4):
+        x = bottleneck(sd, f"backbone.layer1.{b}", x, 1)
+    if taps is not None:
+        taps["hr.layer1"] = x
+    ys = [x]
+    for si, (nmod, nbr) in enumerate(HR_STAGES, start=2):
+        t = f"backbone.transition{si - 1}"
+        xs = []
+        for i in range(nbr):
+            if i < len(ys):
+                if f"{t}.{i}.0.weight" in sd:            # hrnet.py:389-392 / :398-401: stage 2 feeds x, later stages y_list[-1]
+                    xs.append(_conv_bn(sd, f"{t}.{i}.0", f"{t}.{i}.1", ys[0] if si == 2 else ys[-1]))
+                else:
+                    xs.append(ys[i])
+            else:
+                v = ys[0] if si == 2 else ys[-1]
+                j = 0
+                while f"{t}.{i}.{j}.0.weight" in sd:
+                    v = _conv_bn(sd, f"{t}.{i}.{j}.0", f"{t}.{i}.{j}.1", v, stride=2)
+                    j += 1
+                xs.append(v)
+        if taps is not None:
+            for i, v in enumerate(xs):
+                taps[f"hr.stage{si}.in{i}"] = v
+        for m in range(nmod):
+            xs = hr_module(sd, f"backbone.stage{si}.{m}", xs, taps, f"hr.stage{si}.{m}")
+        ys = xs
+    return ys
+
+
 # ----------------------------------------------------------------------------
 # heads
 # ----------------------------------------------------------------------------
@@ -254,11 +414,14 @@ def soft_argmax_2d(heatmap, temperature: float = 1000.0):
     return torch.cat((ex, ey), dim=2)
 
 
-def sample_net(sd, feat, xy, taps=None):
+def sample_net(sd, feat, xy, taps=None, level=0):
     """reference nets.py:55-63 (+ :46-53): dense 1x1 conv+BN+ReLU, then bilinear
-    grid_sample(align_corners=True, zero padding) at the joints."""
-    f = F.relu(_bn(sd, "sample_nets.0.conv.1",
-                   F.conv2d(feat, sd["sample_nets.0.conv.0.weight"], sd["sample_nets.0.conv.0.bias"])))
+    grid_sample(align_corners=True, zero padding) at the joints.  The coordinates are heat-map pixels (0..31) and are
+    normalised by THIS level's own width / height (nets.py:47-49): on the HRNet levels that are not 32 x 32 they
+    therefore address the level's pixels with the same un-rescaled numbers (64 x 64: the top-left quadrant; 16 x 16 and
+    8 x 8: mostly outside the map, i.e. zeros) - the reference's behaviour, reproduced as is."""
+    q = f"sample_nets.{level}"
+    f = F.relu(_bn(sd, q + ".conv.1", F.conv2d(feat, sd[q + ".conv.0.weight"], sd[q + ".conv.0.bias"])))
     h, w = f.shape[2:]
     gx = xy[:, :, 0] / (w - 1) * 2 - 1
     gy = xy[:, :, 1] / (h - 1) * 2 - 1
@@ -426,14 +589,28 @@ def forward(sd, cfg, x, bbox=None, intr=None, return_taps=False, teacher=None):
         raise ValueError(f"input has {v} views, model was built for {nv}")
     pe_list = cfg["model"].get("pos_enc", ["pos2d", "sin"])
     teacher = teacher or {}
-    feat = backbone(sd, x.reshape(-1, c, h, w), taps)
-    if "backbone_out" in teacher:                        # [b*v, 1024, 32, 32]
-        feat = teacher["backbone_out"]
-    hm = pose_net(sd, feat, taps)
-    xy = soft_argmax_2d(hm)
-    if "coords" in teacher:                              # [b*v, 21, 2] heat-map pixels: conditions everything downstream
-        xy = teacher["coords"].reshape(xy.shape).to(xy.dtype)
-    sampled = sample_net(sd, feat, xy, taps)
+    if cfg["model"].get("backbone", "resnet") == "hrnet":    # handmvnet.py:41-56,162,180-187 with the 4-level backbone
+        feats = hrnet_backbone(sd, x.reshape(-1, c, h, w), taps)
+        if "levels" in teacher:
+            feats = list(teacher["levels"])
+        feat = feats[0]
+        hm = F.conv2d(feat, sd["pose_net.weight"], sd["pose_net.bias"], stride=2, padding=1)
+        xy = soft_argmax_2d(hm)
+        if "coords" in teacher:
+            xy = teacher["coords"].reshape(xy.shape).to(xy.dtype)
+        sampled = torch.cat([sample_net(sd, f, xy, None, level=l) for l, f in enumerate(feats)], dim=-1)
+        if taps is not None:
+            for l, f in enumerate(feats):
+                taps[f"level{l}"] = f
+    else:
+        feat = backbone(sd, x.reshape(-1, c, h, w), taps)
+        if "backbone_out" in teacher:                    # [b*v, 1024, 32, 32]
+            feat = teacher["backbone_out"]
+        hm = pose_net(sd, feat, taps)
+        xy = soft_argmax_2d(hm)
+        if "coords" in teacher:                          # [b*v, 21, 2] heat-map pixels: conditions everything downstream
+            xy = teacher["coords"].reshape(xy.shape).to(xy.dtype)
+        sampled = sample_net(sd, feat, xy, taps)
     tok = sampled
     if "pos2d" in pe_list:
         tok = torch.cat([tok, xy], dim=2)

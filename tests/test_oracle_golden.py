@@ -14,7 +14,8 @@ CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(
 
 
 def _run(g):
-    cfg = O.release_config(int(g["meta_num_views"]), bool(g["meta_crop"]))
+    backbone = str(g["meta_backbone"]) if "meta_backbone" in g.files else "resnet"
+    cfg = O.release_config(int(g["meta_num_views"]), bool(g["meta_crop"]), backbone)
     sd = O.make_state_dict(cfg, seed=int(g["meta_seed_w"]), randomize_norm=bool(g["meta_randomize_norm"]))
     x, bbox, intr = O.make_inputs(int(g["meta_batch"]), int(g["meta_num_views"]), seed=int(g["meta_seed_x"]))
     if bool(g["meta_crop"]):
@@ -33,13 +34,14 @@ def test_oracle_matches_reference_fixture(case, golden_dir):
     # outputs (fp32 CPU, same torch build: differences are accumulation-order only)
     hm = out["heatmap"]
     np.testing.assert_array_equal(hm.flatten(-2).argmax(-1).numpy(), g["out_heatmap_argmax"])
-    np.testing.assert_allclose(hm[..., ::4, ::4].numpy(), g["out_heatmap_sub"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(hm[..., ::4, ::4].numpy(), g["out_heatmap_sub"], rtol=1e-4, atol=1e-4 * max(1.0, float(np.abs(g["out_heatmap_sub"]).max())))
     np.testing.assert_allclose(out["joints_crop_img"].numpy(), g["out_joints_crop_img"], rtol=0, atol=1e-3)
     # final keypoints: the north-star criterion is 0.1 mm; the oracle must be far inside it
     assert np.abs(out["joints_cam"].numpy() - g["out_joints_cam"]).max() < 1e-6  # metres
     # every stage fingerprint
-    for key in ("stem", "layer1", "layer2", "backbone_out", "heatmap", "sampled", "tokens",
-                "fusion0", "fusion1", "fusion2", "fusion3", "fusion4", "joints_cam"):
+    keys = [k[len("stage_"):-len("_shape")] for k in g.files if k.startswith("stage_") and k.endswith("_shape")]
+    assert len(keys) >= 12
+    for key in keys:
         t = taps[key]
         assert list(t.shape) == list(g[f"stage_{key}_shape"]), key
         flat = t.reshape(-1)
