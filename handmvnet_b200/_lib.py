@@ -7,7 +7,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libhandmvnet_b200.so")
 
 PRECISION = {"bf16": 0, "fp32": 1}
 STAGE = {"backbone": 0, "pose": 1, "sample": 2, "fusion": 3, "gcn": 4, "softargmax": 5}
-TENSOR = {"feat": 0, "heatmap": 1, "xy": 2, "tokens": 3, "fused": 4, "joints": 5}
+TENSOR = {"feat": 0, "heatmap": 1, "xy": 2, "tokens": 3, "fused": 4, "joints": 5, "feat1": 6, "feat2": 7, "feat3": 8}
+BACKBONE = {"resnet": 0, "hrnet": 1}
 
 # every symbol include/handmvnet_b200.h declares
 EXPORTS = ["hmv_create", "hmv_destroy", "hmv_set_weight", "hmv_prepare", "hmv_forward", "hmv_forward_host",
@@ -21,7 +22,7 @@ EXPORTS = ["hmv_create", "hmv_destroy", "hmv_set_weight", "hmv_prepare", "hmv_fo
 class HmvConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("num_views", "image_size", "heatmap_size", "use_pos2d", "use_crop", "use_sin", "fusion_layers",
-                 "precision", "micro_batch", "device")]
+                 "precision", "micro_batch", "device", "backbone")] + [("hr_channels", ctypes.c_int32 * 4)]
 
 
 _lib = None

@@ -19,10 +19,20 @@ def load_config(yaml_file: str) -> dict:
     return cfg
 
 
-def release_config(num_views: int = 5, crop: bool = True, name: str = "ho3d") -> dict:
-    """In-memory equivalent of configs/release/{HO3D,DexYCB,MVHand}_HandMvNet[_wo_cam].yaml restricted to the
+def release_config(num_views: int = 5, crop: bool = True, name: str = "ho3d", backbone: str = "resnet") -> dict:
+    """In-memory equivalent of configs/release/{HO3D,DexYCB,MVHand}_HandMvNet[_HR][_wo_cam].yaml restricted to the
     keys the forward path reads (the YAML files themselves belong to the reference and are not shipped)."""
     pos_enc = ["pos2d", "crop", "sin"] if crop else ["pos2d", "sin"]
+    if backbone == "hrnet":
+        return {
+            "name": "handmvnet",
+            "data": {"name": name, "batch_size": 16, "heatmap_size": 32, "image_size": 256,
+                     "selected_views": list(range(num_views)), "num_views": num_views},
+            "model": {"selected_views": list(range(num_views)), "num_views": num_views, "fusion": "cross_attn",
+                      "fusion_layers": 5, "pos_enc": pos_enc, "use_gcn": True, "backbone": "hrnet", "backbone_type": "w40",
+                      "backbone_pretrained_path": "", "backbone_channels": [40, 80, 160, 320], "backbone_pretrained": False},
+            "train": {"debug": False, "root_relative": True, "device": "cuda"},
+        }
     return {
         "name": "handmvnet",
         "data": {"name": name, "batch_size": 16, "heatmap_size": 32, "image_size": 256,

@@ -184,7 +184,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 1)) { alive = false; break; }
                         const uint32_t fb = full0 + 8 * stage;
                         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                        mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                        mbar_arrive_expect_tx(fb, static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes);
                         tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
                         if (CL == 2)       // this CTA's half of the weight tile, delivered to both CTAs
                             tma_load_2d_mc(sa + Cfg::kABytes + crank * (Cfg::kBBytes / 2), &tmB, fb, kb * kTcBlockK,
@@ -246,7 +246,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (!mbar_wait(cempty0 + 8 * slot, (use & 1) ^ 1, p.err_flag, 5)) { alive = false; break; }
                     mbar_arrive_expect_tx(cfull0 + 8 * slot, kChunkBytes);
                     tma_load_2d(rbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
-                                m_tile * kTcBlockM);
+                                m_tile * p.tile_rows);
                 }
             }
         }
@@ -262,8 +262,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (!mbar_wait(tfull0 + 8 * acc, acc_phase, p.err_flag, 4)) break;
             tc_fence_after();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            const int row = m_tile * kTcBlockM + quarter * 32 + lane;
-            const bool row_ok = row < p.ep.M;
+            const int row = m_tile * p.tile_rows + quarter * 32 + lane;
+            const bool row_ok = row < p.ep.M && quarter * 32 < p.tile_rows;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r0[16], r1[16];
@@ -361,8 +361,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 named_bar_sync(1 + quarter, 64);           // both column halves of the slab are written
                 if (issuer) {
-                    tma_store_2d(&tmC, sbuf0 + sslot * kChunkBytes + quarter * (32 * 128), n_tile * BN + c * kChunkCols,
-                                 m_tile * kTcBlockM + quarter * 32);
+                    if (quarter * 32 < p.tile_rows)        // (8 x 8 maps: rows 64..127 of the MMA tile hold nothing)
+                        tma_store_2d(&tmC, sbuf0 + sslot * kChunkBytes + quarter * (32 * 128), n_tile * BN + c * kChunkCols,
+                                     m_tile * p.tile_rows + quarter * 32);
                     bulk_commit();
                 }
                 if (!alive) break;
@@ -410,9 +411,10 @@ int tc_init() {
     HMV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     HMV_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
     if (set_attr<32, TC_DIRECT>() || set_attr<64, TC_DIRECT>() || set_attr<128, TC_DIRECT>() || set_attr<176, TC_DIRECT>() ||
-        set_attr<256, TC_DIRECT>() || set_attr<64, TC_STORE>() || set_attr<128, TC_STORE>() || set_attr<256, TC_STORE>() ||
-        set_attr<64, TC_STORE_DEEP>() || set_attr<128, TC_STORE_DEEP>() || set_attr<256, TC_STORE_DEEP>() ||
-        set_attr<64, TC_STORE_RES>() || set_attr<128, TC_STORE_RES>() || set_attr<256, TC_STORE_RES>())
+        set_attr<192, TC_DIRECT>() || set_attr<256, TC_DIRECT>() ||
+        set_attr<64, TC_STORE>() || set_attr<128, TC_STORE>() || set_attr<192, TC_STORE>() || set_attr<256, TC_STORE>() ||
+        set_attr<64, TC_STORE_DEEP>() || set_attr<128, TC_STORE_DEEP>() || set_attr<192, TC_STORE_DEEP>() || set_attr<256, TC_STORE_DEEP>() ||
+        set_attr<64, TC_STORE_RES>() || set_attr<128, TC_STORE_RES>() || set_attr<192, TC_STORE_RES>() || set_attr<256, TC_STORE_RES>())
         return 1;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
@@ -466,6 +468,7 @@ int tc_pick_bn(int n) {
     if (n <= 64) return 64;
     if (n <= 128) return 128;
     if (n % 256 == 0) return 256;
+    if (n % 192 == 0) return 192;   // HRNet-w40 widths padded: 160 -> 192, 320 -> 2 x 192 (the store clips at the tensor's 320 columns)
     if (n % 176 == 0) return 176;   // 528 = 3 x 176 (d_model 524 padded)
     if (n % 128 == 0) return 128;
     return 0;
@@ -527,6 +530,7 @@ int tc_launch(const TcLaunch& l, int num_sms, cudaStream_t stream) {
         case 64: return launch_mode<64>(l, num_sms, stream);
         case 128: return launch_mode<128>(l, num_sms, stream);
         case 176: return launch_mode<176>(l, num_sms, stream);
+        case 192: return launch_mode<192>(l, num_sms, stream);
         case 256: return launch_mode<256>(l, num_sms, stream);
     }
     set_error("tc_launch: unsupported BN " + std::to_string(l.bn));

@@ -35,6 +35,8 @@ struct TcParams {
     int num_taps, cblks;               // K blocks per tile = num_taps * cblks
     int flat;                          // 1: A is [M, K] (coord1 = m_tile*128); 0: spatial tile
     int tpi, hbox;                     // spatial: tiles per image, rows of H' per tile
+    int a_bytes;                       // bytes one A box delivers (16 KiB; less when an image has fewer than 128 pixels: 8 x 8 maps)
+    int tile_rows;                     // output rows a tile owns (128; 64 for 8 x 8 maps: the upper half of the MMA tile is unused)
     TcTap taps[kTcMaxTaps];
     Epilogue ep;
     int* err_flag;                     // set to non-zero on an mbarrier timeout

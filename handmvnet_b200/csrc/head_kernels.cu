@@ -215,19 +215,22 @@ __global__ void tokens_kernel(const TokenParams p) {
     const int row = blockIdx.x;                // n * 21 + j
     const int n = row / kJoints;
     const int pos = row % p.tokens_per_sample; // token index inside the sample (view-major)
-    const float* g = p.g + static_cast<size_t>(row) * 4 * p.ldg;
-    const float w0 = p.wts[row * 4], w1 = p.wts[row * 4 + 1], w2 = p.wts[row * 4 + 2], w3 = p.wts[row * 4 + 3];
     float* of = p.tok_f32 + static_cast<size_t>(row) * p.pitch;
     T* ol = p.tok_lp ? static_cast<T*>(p.tok_lp) + static_cast<size_t>(row) * p.pitch : nullptr;
     const float* pe = p.pe ? p.pe + static_cast<size_t>(pos) * p.d : nullptr;
     for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
         float v;
         if (c < p.feat) {
+            int l = 0, cl = c;                   // feature level and column inside it (levels are concatenated: handmvnet.py:187)
+            while (l + 1 < p.n_src && cl >= p.src[l].width) { cl -= p.src[l].width; ++l; }
+            const TokenSource& sl = p.src[l];
+            const float* g = sl.g + static_cast<size_t>(row) * 4 * sl.ldg;
+            const float* w = sl.wts + row * 4;
             v = 0.f;
-            v += g[c] * w0;
-            v += g[p.ldg + c] * w1;
-            v += g[2 * p.ldg + c] * w2;
-            v += g[3 * p.ldg + c] * w3;
+            v += g[cl] * w[0];
+            v += g[sl.ldg + cl] * w[1];
+            v += g[2 * sl.ldg + cl] * w[2];
+            v += g[3 * sl.ldg + cl] * w[3];
         } else {
             int e = c - p.feat;
             if (p.use_pos2d && e < 2) {
@@ -877,6 +880,116 @@ preprocess_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ bb
         __threadfence_system();
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// HRNet pieces (reference backbones/hrnet.py)
+// ------------------------------------------------------------------------------------------------
+// One CTA = one output row of one image; one thread = one output pixel, all 64 output channels in registers.  The three
+// input rows (zero padded) and the 64 x 27 weights live in shared memory; weights are read as warp-wide broadcasts.
+template <typename T>
+__global__ void __launch_bounds__(128) hr_stem_kernel(const void* __restrict__ xin, int x_is_u8, StemNorm norm, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, T* __restrict__ out, int size) {
+    pdl_wait();
+    extern __shared__ float hs_smem[];
+    const int wout = size / 2;
+    float* sw = hs_smem;                         // [27][64]  (tap-major so that a thread's 64 outputs read consecutive floats)
+    float* sb = sw + 27 * 64;                    // [64]
+    float* sx = sb + 64;                         // [3 channels][3 rows][size + 2]
+    const int oy = blockIdx.x, n = blockIdx.y;
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) { const int co = i / 27, t = i % 27; sw[t * 64 + co] = w[i]; }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
+    const int pitch = size + 2;
+    for (int i = threadIdx.x; i < 9 * pitch; i += blockDim.x) {
+        const int c = i / (3 * pitch), r = (i / pitch) % 3, col = i % pitch;
+        const int iy = 2 * oy - 1 + r, ix = col - 1;
+        float v = 0.f;
+        if (iy >= 0 && iy < size && ix >= 0 && ix < size) {
+            const size_t idx = ((static_cast<size_t>(n) * 3 + c) * size + iy) * size + ix;
+            if (x_is_u8) v = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(static_cast<const uint8_t*>(xin)[idx]), 255.f), norm.mean[c]), norm.std[c]);
+            else v = static_cast<const float*>(xin)[idx];
+        }
+        sx[i] = v;
+    }
+    __syncthreads();
+    for (int ox = threadIdx.x; ox < wout; ox += blockDim.x) {
+        float acc[64];
+#pragma unroll
+        for (int co = 0; co < 64; ++co) acc[co] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float a = sx[(c * 3 + r) * pitch + 2 * ox + s2];
+                    const float4* wt = reinterpret_cast<const float4*>(sw + ((r * 3 + s2) * 3 + c) * 64);   // weight layout [cout][r][s][cin] -> tap index (r*3+s)*3+c
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 wv = wt[q];
+                        acc[4 * q] = fmaf(a, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, wv.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(a, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, wv.w, acc[4 * q + 3]);
+                    }
+                }
+        T* o = out + ((static_cast<size_t>(n) * wout + oy) * wout + ox) * 64;
+#pragma unroll
+        for (int co = 0; co < 64; ++co) o[co] = from_f<T>(fmaxf(acc[co] + sb[co], 0.f));
+    }
+}
+
+template <typename T>
+int hr_stem_launch(const void* x, bool x_is_u8, const StemNorm& norm, const float* w, const float* bias, T* out, int n_img, int size,
+                   cudaStream_t s) {
+    if (n_img == 0) return 0;
+    const size_t smem = (27 * 64 + 64 + 9 * (size + 2)) * sizeof(float);
+    HMV_CUDA(launch_kernel(hr_stem_kernel<T>, dim3(size / 2, n_img), dim3(128), smem, s, x, x_is_u8 ? 1 : 0, norm, w, bias, out, size));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int hr_stem_launch<bf16>(const void*, bool, const StemNorm&, const float*, const float*, bf16*, int, int, cudaStream_t);
+template int hr_stem_launch<float>(const void*, bool, const StemNorm&, const float*, const float*, float*, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void fuse_sum_kernel(const FuseSumParams p, size_t total) {
+    pdl_wait();
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = p.C / VEC;
+    const int c = static_cast<int>(idx % cv) * VEC;
+    const int x = static_cast<int>((idx / cv) % p.W);
+    const int y = static_cast<int>((idx / (static_cast<size_t>(cv) * p.W)) % p.H);
+    const size_t n = idx / (static_cast<size_t>(cv) * p.W * p.H);
+    float v[VEC];
+    auto add = [&](const T* src, bool first) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+        const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = first ? to_f(e[i]) : v[i] + to_f(e[i]);
+    };
+    add(static_cast<const T*>(p.base) + ((n * p.H + y) * p.W + x) * p.C + c, true);
+    for (int k = 0; k < p.n_up; ++k) {               // hrnet.py:226-230 adds the branches in ascending order
+        const int sh = p.shift[k], hs = p.H >> sh, ws = p.W >> sh;
+        add(static_cast<const T*>(p.up[k]) + ((n * hs + (y >> sh)) * ws + (x >> sh)) * p.C + c, false);
+    }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) oe[i] = from_f<T>(p.relu ? fmaxf(v[i], 0.f) : v[i]);
+    *reinterpret_cast<uint4*>(static_cast<T*>(p.out) + ((n * p.H + y) * p.W + x) * p.C + c) = o;
+}
+
+template <typename T>
+int fuse_sum_launch(const FuseSumParams& p, cudaStream_t s) {
+    if (p.n_img == 0) return 0;
+    constexpr int VEC = 16 / sizeof(T);
+    HMV_CHECK(p.C % VEC == 0 && p.n_up >= 0 && p.n_up <= 3, "fuse_sum: bad geometry");
+    const size_t total = static_cast<size_t>(p.n_img) * p.H * p.W * (p.C / VEC);
+    HMV_CUDA(launch_kernel(fuse_sum_kernel<T>, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, p, total));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+template int fuse_sum_launch<bf16>(const FuseSumParams&, cudaStream_t);
+template int fuse_sum_launch<float>(const FuseSumParams&, cudaStream_t);
 
 int preprocess_launch(const uint8_t* frames, const int* bbox, float* out, int n_img, int frame_h, int frame_w, int size,
                       const StemNorm& norm, int* err_flag, cudaStream_t s) {

@@ -47,10 +47,15 @@ template <typename T>
 int sample_gather_launch(const T* feat, const float* xy, T* rows, float* wts, int n_img, int H, int W, int C,
                          cudaStream_t s);
 
-struct TokenParams {
-    const float* g;        // [n_img*21*4, ldg] sampled conv+BN+ReLU rows (fp32)
+struct TokenSource {       // one feature level's sampled rows (the ResNet configs have one level, HRNet four: handmvnet.py:185-187)
+    const float* g;        // [n_img*21*4, ldg] conv+BN+ReLU of the 4 bilinear neighbours of every joint (fp32)
+    const float* wts;      // [n_img*21*4] bilinear weights on THIS level (0 for neighbours outside the map)
     int ldg;
-    const float* wts;      // [n_img*21*4]
+    int width;             // feature columns this level contributes (c_level / 2)
+};
+struct TokenParams {
+    TokenSource src[4];
+    int n_src;
     const float* xy;       // [n_img*21*2]
     const float* bbox;     // [n_img*4] xyxy or null
     const float* intr;     // [n_img*4] fx fy cx cy or null
@@ -110,5 +115,25 @@ struct GcnParams {
 };
 // h1_scratch: [batch, 21, 256] fp32 workspace for the first layer's output
 int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s);
+
+// ---- HRNet backbone pieces (reference backbones/hrnet.py) ---------------------------------------------------------
+// First stem conv: 3x3 / stride 2 / pad 1, 3 -> 64 channels, + folded BN + ReLU (hrnet.py:244-245,380-382), straight from
+// the fp32 (or uint8, normalised on the fly) NCHW input to an NHWC activation.  w: [64][27] (tap-major (r, s), channel
+// minor) fp32, bias [64].  CUDA cores: K = 27 is no tensor-core shape.
+template <typename T>
+int hr_stem_launch(const void* x, bool x_is_u8, const StemNorm& norm, const float* w, const float* bias, T* out, int n_img, int size,
+                   cudaStream_t s);
+// Branch fusion (hrnet.py:222-231): out = [relu](base + sum_k nearest_upsample(up[k], 2^shift[k])), NHWC with `C` channels
+// (a multiple of 8); up[k] is [n, H >> shift, W >> shift, C].
+struct FuseSumParams {
+    const void* base;
+    const void* up[3];
+    int shift[3];
+    int n_up;
+    void* out;
+    int n_img, H, W, C, relu;
+};
+template <typename T>
+int fuse_sum_launch(const FuseSumParams& p, cudaStream_t s);
 
 }  // namespace hmv

@@ -30,23 +30,26 @@ bool pdl_enabled() {
 // ------------------------------------------------------------------------------------------------
 // layout conversion utilities (stage import/export, unit-test entry point)
 // ------------------------------------------------------------------------------------------------
+// `ld` = channel pitch of the NHWC buffer (>= C; HRNet-w40 buffers are wider than the layer, extra channels are zero)
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int C, int HW, size_t total) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int C, int HW, size_t total, int ld = 0) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over NCHW output
     if (idx >= total) return;
+    if (ld == 0) ld = C;
     const int p = static_cast<int>(idx % HW);
     const int c = static_cast<int>((idx / HW) % C);
     const size_t n = idx / (static_cast<size_t>(HW) * C);
-    out[idx] = to_f(in[(n * HW + p) * C + c]);
+    out[idx] = to_f(in[(n * HW + p) * ld + c]);
 }
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int HW, size_t total) {
-    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over NHWC output
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int HW, size_t total, int ld = 0) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over the (pitched) NHWC output; total = n * HW * ld
     if (idx >= total) return;
-    const int c = static_cast<int>(idx % C);
-    const int p = static_cast<int>((idx / C) % HW);
-    const size_t n = idx / (static_cast<size_t>(HW) * C);
-    out[idx] = from_f<T>(in[(n * C + c) * HW + p]);
+    if (ld == 0) ld = C;
+    const int c = static_cast<int>(idx % ld);
+    const int p = static_cast<int>((idx / ld) % HW);
+    const size_t n = idx / (static_cast<size_t>(HW) * ld);
+    out[idx] = c < C ? from_f<T>(in[(n * C + c) * HW + p]) : from_f<T>(0.f);
 }
 // dense fp32 [rows, d] <-> pitched fp32 (+ optional low-precision copy)
 template <typename T>
@@ -94,11 +97,12 @@ struct HostTensor {
     std::vector<int64_t> dims;
 };
 
-enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4, SK_SEAM = 5 };
+enum StepKind { SK_PACK = 0, SK_GEMM = 1, SK_MAXPOOL = 2, SK_STEM_POOL = 3, SK_TAIL = 4, SK_SEAM = 5, SK_HR_STEM = 6, SK_FUSE_SUM = 7 };
 struct StepIO {                                    // one activation tensor a backbone step reads / writes (NHWC in the workspace)
     void* ptr;
     std::string tap;                              // name of the oracle tap holding the same tensor (oracle.backbone(per_layer=True))
     int C, H, W;
+    int ld = 0;                                   // channel pitch of the buffer (0 = C)
 };
 struct Step {
     int kind;
@@ -108,6 +112,7 @@ struct Step {
     void* out = nullptr;
     int C = 0, H = 0, W = 0;                      // output geometry (NHWC)
     std::vector<StepIO> ins, outs;                // teacher-forced single-step runs (hmv_debug_step_run)
+    FuseSumParams fuse{};                         // SK_FUSE_SUM
 };
 
 // conv2 + conv3 (+residual) of one bottleneck as a single launch (bottleneck_tc.cu)
@@ -170,6 +175,15 @@ struct hmv_handle {
     float* gcn_h1 = nullptr;
     void* stem_w = nullptr;                       // fused stem (bf16 path): packed weights + folded-BN bias
     float* stem_b = nullptr;
+    // HRNet backbone (cfg.backbone == HMV_BACKBONE_HRNET): four feature levels, level l is [n, 64 >> l, 64 >> l, hr_cp[l]]
+    bool hr = false;
+    int hr_c[4] = {0, 0, 0, 0}, hr_cp[4] = {0, 0, 0, 0};   // real / buffer channel counts (tensor-core path pads 40/80/160 to 64/128/192)
+    void* hr_lvl[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* hr_stem_w = nullptr;                   // first stem conv [64][27] fp32 (CUDA-core kernel)
+    int hr_samp[4] = {-1, -1, -1, -1};            // per-level SampleNet conv layers
+    void* hr_rows[4] = {nullptr, nullptr, nullptr, nullptr};    // gathered neighbour rows per level
+    float* hr_g[4] = {nullptr, nullptr, nullptr, nullptr};      // sampled conv outputs per level (fp32)
+    float* hr_wts[4] = {nullptr, nullptr, nullptr, nullptr};    // bilinear weights per level
     // uint8 inputs (hmv_forward_u8 / hmv_forward_host_u8_async): normalised inside the stem kernel
     bool x_u8 = false;                            // element type of the x pointer of the call being enqueued
     StemNorm norm{{0.485f, 0.456f, 0.406f}, {0.229f, 0.224f, 0.225f}};   // datasets/ho3d.py:35-40
@@ -346,8 +360,8 @@ static int finish_layer(hmv_handle* h, Layer& L, const std::vector<float>& wmat,
     L.bias_host = bp;
     L.ep.bias = L.bias;
     L.ep.N = L.cout;
-    HMV_CHECK(!h->bf16 || L.ep.out_mode == OUT_F32_NCHW || L.ep.ldc >= L.n_alloc,
-              "row-major output pitch must cover the padded tile width in " + L.name);
+    // (a row-major pitch below the padded tile width is only legal on the TMA-store path, which clips at the tensor's
+    //  columns: checked in build_tc once the epilogue variant is known)
     return 0;
 }
 
@@ -360,6 +374,8 @@ static int build_tc(hmv_handle* h, Layer& L) {
     t.bn = L.bn;
     t.p.num_n_tiles = L.n_alloc / L.bn;
     t.p.err_flag = h->err_flag_dev;
+    t.p.a_bytes = kTcBlockM * kTcBlockK * 2;
+    t.p.tile_rows = kTcBlockM;
     uint64_t dims[5], strides[4];
     uint32_t box[5];
     const uint64_t N = static_cast<uint64_t>(L.max_units);
@@ -373,23 +389,29 @@ static int build_tc(hmv_handle* h, Layer& L) {
         t.p.taps[0] = TcTap{0, 0, 0, 0};
     } else if (L.kind == LK_CONV3_S1) {
         const uint64_t C = L.cin, W = L.win, H = L.hin;
-        HMV_CHECK(128 % L.win == 0 && L.hin % (128 / L.win) == 0 && L.cin % 64 == 0, "conv3x3: unsupported geometry");
+        const bool small = L.hin * L.win < 128;            // an image is smaller than a tile (8 x 8 maps): one image per tile, 64 rows used
+        HMV_CHECK(128 % L.win == 0 && (small || L.hin % (128 / L.win) == 0) && L.cin % 64 == 0 && (!small || L.hin * L.win == 64),
+                  "conv3x3: unsupported geometry");
         dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
         strides[0] = C * 2; strides[1] = W * C * 2; strides[2] = W * C * 2; strides[3] = H * W * C * 2;
-        box[0] = 64; box[1] = L.win; box[2] = 1; box[3] = 128 / L.win; box[4] = 1;
-        t.p.flat = 0; t.p.hbox = 128 / L.win; t.p.tpi = L.hin / t.p.hbox;
+        box[0] = 64; box[1] = L.win; box[2] = 1; box[3] = small ? L.hin : 128 / L.win; box[4] = 1;
+        t.p.flat = 0; t.p.hbox = static_cast<int>(box[3]); t.p.tpi = L.hin / t.p.hbox;
+        if (small) { t.p.tile_rows = L.hin * L.win; t.p.a_bytes = L.hin * L.win * kTcBlockK * 2; }
         t.p.num_taps = 9; t.p.cblks = L.cin / 64;
         for (int r = 0; r < 3; ++r)
             for (int s = 0; s < 3; ++s) t.p.taps[r * 3 + s] = TcTap{0, s - 1, 0, r - 1};
     } else if (L.kind == LK_CONV_S2) {
         // input [N, H, W, C] addressed as (2C | W/2 | row parity | H/2 | N)
         const uint64_t C = L.cin, W = L.win, H = L.hin;
-        HMV_CHECK(L.win % 2 == 0 && L.hin % 2 == 0 && 128 % L.wout == 0 && L.hout % (128 / L.wout) == 0 && L.cin % 64 == 0,
+        const bool small = L.hout * L.wout < 128;
+        HMV_CHECK(L.win % 2 == 0 && L.hin % 2 == 0 && 128 % L.wout == 0 && (small || L.hout % (128 / L.wout) == 0) && L.cin % 64 == 0 &&
+                      (!small || L.hout * L.wout == 64),
                   "stride-2 conv: unsupported geometry");
         dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
         strides[0] = 2 * C * 2; strides[1] = W * C * 2; strides[2] = 2 * W * C * 2; strides[3] = H * W * C * 2;
-        box[0] = 64; box[1] = L.wout; box[2] = 1; box[3] = 128 / L.wout; box[4] = 1;
-        t.p.flat = 0; t.p.hbox = 128 / L.wout; t.p.tpi = L.hout / t.p.hbox;
+        box[0] = 64; box[1] = L.wout; box[2] = 1; box[3] = small ? L.hout : 128 / L.wout; box[4] = 1;
+        t.p.flat = 0; t.p.hbox = static_cast<int>(box[3]); t.p.tpi = L.hout / t.p.hbox;
+        if (small) { t.p.tile_rows = L.hout * L.wout; t.p.a_bytes = L.hout * L.wout * kTcBlockK * 2; }
         t.p.cblks = L.cin / 64;
         if (L.ksize == 1) {
             t.p.num_taps = 1;
@@ -409,7 +431,7 @@ static int build_tc(hmv_handle* h, Layer& L) {
     }
     // wide, K-deep layers run as 2-CTA clusters that share multicast weight tiles (conv_gemm_tc.cu, CL = 2)
     static const int cluster_min_k = [] { const char* e = getenv("HMV_CLUSTER_MINK"); return e ? atoi(e) : 512; }();
-    t.cluster = (L.bn == 256 && L.K >= cluster_min_k && h->use_clusters) ? 2 : 1;
+    t.cluster = (L.bn == 256 && L.K >= cluster_min_k && h->use_clusters && t.p.tile_rows == kTcBlockM) ? 2 : 1;
     if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster == 2 ? L.bn / 2 : L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
         return 1;
@@ -433,6 +455,8 @@ static int build_tc(hmv_handle* h, Layer& L) {
             }
         }
     }
+    HMV_CHECK(t.mode != TC_DIRECT || L.ep.out_mode == OUT_F32_NCHW || L.ep.ldc >= L.n_alloc,
+              "row-major output pitch must cover the padded tile width in " + L.name);
     return 0;
 }
 
@@ -575,12 +599,25 @@ static Epilogue make_ep(void* out, int ldc, int out_mode, int act) {
 }
 
 // A conv layer from already-folded weights wf[cout][k*k][cin], bf[cout].  in: NHWC activations.
-static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vector<float>& wf, const std::vector<float>& bf,
+// cin_pad / cout_pad (0 = none): channel counts of the NHWC buffers when they are wider than the layer (HRNet-w40 widths
+// 40 / 80 / 160 live in 64 / 128 / 192-channel buffers on the tensor-core path; the extra weights and biases are zero, so
+// the extra output channels stay exactly zero).
+static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vector<float>& wf_in, const std::vector<float>& bf,
                         int cin, int cout, int k, int stride, int hin, int win, const void* in, void* out, int act,
-                        const void* residual, int* index, int nchw_hw = 0) {
+                        const void* residual, int* index, int nchw_hw = 0, int cin_pad = 0, int cout_pad = 0) {
+    if (cin_pad < cin) cin_pad = cin;
+    if (cout_pad < cout) cout_pad = cout;
+    std::vector<float> wpad;
+    if (cin_pad != cin) {                             // [cout][k*k][cin] -> [cout][k*k][cin_pad]
+        wpad.assign(static_cast<size_t>(cout) * k * k * cin_pad, 0.f);
+        for (int co = 0; co < cout; ++co)
+            for (int t = 0; t < k * k; ++t)
+                memcpy(&wpad[(static_cast<size_t>(co) * k * k + t) * cin_pad], &wf_in[(static_cast<size_t>(co) * k * k + t) * cin], sizeof(float) * cin);
+    }
+    const std::vector<float>& wf = cin_pad != cin ? wpad : wf_in;
     Layer L;
     L.name = name;
-    L.cin = cin; L.cout = cout; L.ksize = k; L.stride = stride; L.pad = k / 2;
+    L.cin = cin_pad; L.cout = cout; L.ksize = k; L.stride = stride; L.pad = k / 2;
     L.hin = hin; L.win = win; L.hout = hin / stride; L.wout = win / stride;
     L.max_units = h->mb_img;
     L.in = in;
@@ -588,17 +625,18 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
     else if (k == 3 && stride == 1) { L.kind = LK_CONV3_S1; }
     else if (stride == 2 && (k == 1 || k == 3)) { L.kind = LK_CONV_S2; }
     else { HMV_CHECK(false, "unsupported conv geometry for " + name); }
-    L.K = k * k * cin;
+    L.K = k * k * cin_pad;
     HMV_CHECK(!h->bf16 || L.K % 64 == 0, "tensor-core path needs Cin to be a multiple of 64 in " + name);
-    HMV_CHECK(cin % 4 == 0, "Cin must be a multiple of 4 in " + name);
-    L.bn = tc_pick_bn(cout);
+    HMV_CHECK(cin_pad % 4 == 0, "Cin must be a multiple of 4 in " + name);
+    L.bn = tc_pick_bn(nchw_hw > 0 ? cout : cout_pad);
+    if (L.bn == 0) L.bn = tc_pick_bn((cout_pad + 191) / 192 * 192);
     HMV_CHECK(L.bn > 0, "no tile width for " + name);
-    L.n_alloc = (cout + L.bn - 1) / L.bn * L.bn;
-    if (!h->bf16) L.n_alloc = (cout + 3) / 4 * 4;
-    L.ep = make_ep(out, cout, h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR, act);
+    L.n_alloc = ((nchw_hw > 0 ? cout : cout_pad) + L.bn - 1) / L.bn * L.bn;
+    if (!h->bf16) L.n_alloc = (cout_pad + 3) / 4 * 4;
+    L.ep = make_ep(out, cout_pad, h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR, act);
     if (nchw_hw > 0) { L.ep.out_mode = OUT_F32_NCHW; L.ep.hw = nchw_hw; }     // fp32 [n_img, cout, hw] output
     if (residual) {
-        L.ep.residual = residual; L.ep.res_mode = h->bf16 ? RES_BF16 : RES_F32; L.ep.res_ld = cout;
+        L.ep.residual = residual; L.ep.res_mode = h->bf16 ? RES_BF16 : RES_F32; L.ep.res_ld = cout_pad;
     }
     if (finish_layer(h, L, wf, bf)) return 1;
     if (h->bf16 && build_tc(h, L)) return 1;
@@ -610,10 +648,10 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
 // A backbone / head conv with its BatchNorm folded from the state_dict.
 static int add_conv(hmv_handle* h, const std::string& name, const std::string& conv_key, const std::string& bn_key,
                     bool has_bias, int cin, int cout, int k, int stride, int hin, int win, const void* in, void* out,
-                    int act, const void* residual, int* index) {
+                    int act, const void* residual, int* index, int cin_pad = 0, int cout_pad = 0) {
     std::vector<float> wf, bf;
     if (fold_conv(h, conv_key, bn_key, has_bias, cout, cin, k, wf, bf)) return 1;
-    return add_conv_raw(h, name, wf, bf, cin, cout, k, stride, hin, win, in, out, act, residual, index);
+    return add_conv_raw(h, name, wf, bf, cin, cout, k, stride, hin, win, in, out, act, residual, index, 0, cin_pad, cout_pad);
 }
 
 // A linear layer y = x W^T + b on [rows, K] with K zero-padded to k_pad.
@@ -844,6 +882,199 @@ static int build_backbone(hmv_handle* h) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// HRNet-w40 / w64 backbone plan (reference backbones/hrnet.py:241-409; the `*_HR*` release configs)
+// ------------------------------------------------------------------------------------------------
+// Every convolution runs through the same implicit-GEMM kernels as the ResNet path (3x3 stride 1 / 2 and 1x1 classes,
+// BN folded, ReLU / residual in the epilogue); the branch-fusion sums (hrnet.py:222-231) are built as
+//   out_i = relu( x_i + sum_{j<i} chain_ij(x_j)  [each chain's last conv adds the running sum as its residual]
+//                     + sum_{j>i} nearest_up(conv1x1_ij(x_j)) [one elementwise kernel] )
+// - the reference's summation order up to fp32 re-association.  On the tensor-core path the w40 widths 40 / 80 / 160
+// live in 64 / 128 / 192-channel NHWC buffers whose extra channels are exactly zero (zero weights and biases).
+static int hr_alloc(hmv_handle* h, void** p, int level, int cp) {
+    const size_t res = static_cast<size_t>(64 >> level);
+    return dev_alloc(h, p, static_cast<size_t>(h->mb_img) * res * res * cp * h->esz);
+}
+
+static int add_fuse_step(hmv_handle* h, const std::string& name, const void* base, std::vector<std::pair<const void*, int>> ups, void* out,
+                         int level, int cp, int c_real, bool relu, std::vector<StepIO> ins) {
+    Step st;
+    st.kind = SK_FUSE_SUM; st.name = name; st.out = out; st.C = c_real; st.H = 64 >> level; st.W = 64 >> level;
+    st.fuse.base = base; st.fuse.out = out; st.fuse.n_up = static_cast<int>(ups.size());
+    for (size_t k = 0; k < ups.size(); ++k) { st.fuse.up[k] = ups[k].first; st.fuse.shift[k] = ups[k].second; }
+    st.fuse.H = 64 >> level; st.fuse.W = 64 >> level; st.fuse.C = cp; st.fuse.relu = relu ? 1 : 0;
+    st.ins = std::move(ins);
+    st.outs.push_back({out, name, c_real, 64 >> level, 64 >> level});
+    h->backbone.push_back(st);
+    return 0;
+}
+
+static int build_hrnet(hmv_handle* h) {
+    const int R0 = h->img / 4;                        // 64
+    HMV_CHECK(R0 == 64, "the HRNet plan is built for 256 x 256 inputs");
+    auto cpad = [&](int c) { return !h->bf16 ? c : (c <= 64 ? 64 : c <= 128 ? 128 : c <= 192 ? 192 : (c + 63) / 64 * 64); };
+    // ---- stem (hrnet.py:244-247, 380-385): conv3x3/2 3->64 (CUDA cores), conv3x3/2 64->64 ----
+    void *s1 = nullptr, *s2 = nullptr;
+    if (dev_alloc(h, &s1, static_cast<size_t>(h->mb_img) * 128 * 128 * 64 * h->esz) || hr_alloc(h, &s2, 0, 64)) return 1;
+    {
+        std::vector<float> wf, bf;
+        if (fold_conv(h, "backbone.conv1", "backbone.bn1", false, 64, 3, 3, wf, bf)) return 1;
+        if (upload_f32(h, &h->hr_stem_w, wf) || upload_f32(h, &h->stem_b, bf)) return 1;
+        Step st; st.kind = SK_HR_STEM; st.name = "hr.conv1"; st.out = s1; st.C = 64; st.H = 128; st.W = 128;
+        st.outs.push_back({s1, "hr.conv1", 64, 128, 128});
+        h->backbone.push_back(st);
+    }
+    int idx;
+    if (add_conv(h, "hr.conv2", "backbone.conv2", "backbone.bn2", false, 64, 64, 3, 2, 128, 128, s1, s2, ACT_RELU, nullptr, &idx)) return 1;
+    add_gemm_step(h, "hr.conv2", idx, s2, 64, 64, 64, {{s1, "hr.conv1", 64, 128, 128}});
+    // ---- stage 1: 4 Bottlenecks of 64 planes at 64 x 64 (hrnet.py:249-253) ----
+    void *bx = nullptr, *by = nullptr, *bt1 = nullptr, *bt2 = nullptr, *bds = nullptr;
+    if (hr_alloc(h, &bx, 0, 256) || hr_alloc(h, &by, 0, 256) || hr_alloc(h, &bt1, 0, 64) || hr_alloc(h, &bt2, 0, 64) || hr_alloc(h, &bds, 0, 256)) return 1;
+    void* cur = s2; std::string cur_name = "hr.conv2"; int C = 64;
+    for (int b = 0; b < 4; ++b) {
+        const std::string p = "backbone.layer1." + std::to_string(b), sp = "hr.layer1." + std::to_string(b);
+        void* nxt = (cur == bx) ? by : bx;
+        if (add_conv(h, sp + ".conv1", p + ".conv1", p + ".bn1", false, C, 64, 1, 1, 64, 64, cur, bt1, ACT_RELU, nullptr, &idx)) return 1;
+        add_gemm_step(h, sp + ".conv1", idx, bt1, 64, 64, 64, {{cur, cur_name, C, 64, 64}});
+        if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, 64, 64, 3, 1, 64, 64, bt1, bt2, ACT_RELU, nullptr, &idx)) return 1;
+        add_gemm_step(h, sp + ".conv2", idx, bt2, 64, 64, 64, {{bt1, sp + ".conv1", 64, 64, 64}});
+        const void* res = cur; StepIO res_io{cur, cur_name, C, 64, 64};
+        if (b == 0) {
+            if (add_conv(h, sp + ".downsample", p + ".downsample.0", p + ".downsample.1", false, C, 256, 1, 1, 64, 64, cur, bds, ACT_NONE, nullptr, &idx)) return 1;
+            add_gemm_step(h, sp + ".downsample", idx, bds, 256, 64, 64, {{cur, cur_name, C, 64, 64}});
+            res = bds; res_io = StepIO{bds, sp + ".downsample", 256, 64, 64};
+        }
+        if (add_conv(h, sp + ".conv3", p + ".conv3", p + ".bn3", false, 64, 256, 1, 1, 64, 64, bt2, nxt, ACT_RELU, res, &idx)) return 1;
+        add_gemm_step(h, sp + ".conv3", idx, nxt, 256, 64, 64, {{bt2, sp + ".conv2", 64, 64, 64}, res_io});
+        cur = nxt; cur_name = sp + ".conv3"; C = 256;
+    }
+    // ---- stages 2..4 ----
+    const int stages[3][2] = {{1, 2}, {4, 3}, {3, 4}};   // (modules, branches): hrnet.py:453-485
+    struct Br { void *x = nullptr, *y = nullptr, *t = nullptr, *z = nullptr, *r = nullptr, *d = nullptr; int c = 0, cp = 0; std::string name; };
+    Br br[4];
+    for (int l = 0; l < 4; ++l) {
+        br[l].c = h->hr_c[l]; br[l].cp = cpad(br[l].c);
+        HMV_CHECK(br[l].cp == h->hr_cp[l], "HRNet channel padding mismatch");
+        // x / y: block ping-pong, t: BasicBlock temp, z: fused output, r: running sum of the down chains, d: chain intermediate (<= widest source)
+        if (hr_alloc(h, &br[l].x, l, br[l].cp) || hr_alloc(h, &br[l].y, l, br[l].cp) || hr_alloc(h, &br[l].t, l, br[l].cp) ||
+            hr_alloc(h, &br[l].z, l, br[l].cp) || hr_alloc(h, &br[l].r, l, br[l].cp) || hr_alloc(h, &br[l].d, l, 512))
+            return 1;
+    }
+    void* up[4][4] = {};                                  // up[i][j]: conv1x1_ij(x_j) at resolution j with cp_i channels
+    for (int i = 0; i < 4; ++i) for (int j = i + 1; j < 4; ++j) if (hr_alloc(h, &up[i][j], j, br[i].cp)) return 1;
+    int nprev = 1;                                        // branches alive before the stage
+    void* prev_last = cur; std::string prev_last_name = cur_name; int prev_last_c = 256, prev_last_cp = 256, prev_last_level = 0;
+    for (int si = 0; si < 3; ++si) {
+        const int nmod = stages[si][0], nbr = stages[si][1];
+        const std::string t = "backbone.transition" + std::to_string(si + 1);
+        // transitions (hrnet.py:318-345, 387-408)
+        for (int i = 0; i < nbr; ++i) {
+            const std::string tn = "hr.stage" + std::to_string(si + 2) + ".in" + std::to_string(i);
+            const int res_i = 64 >> i;
+            if (i < nprev) {
+                if (find_w(h, t + "." + std::to_string(i) + ".0.weight")) {     // only transition1.0 in w40 / w64 (256 -> c0)
+                    HMV_CHECK(si == 0 && i == 0, "unexpected transition layer on an existing branch");
+                    if (add_conv(h, tn, t + ".0.0", t + ".0.1", false, prev_last_c, br[0].c, 3, 1, 64, 64, prev_last, br[0].x, ACT_RELU, nullptr, &idx,
+                                 prev_last_cp, br[0].cp)) return 1;
+                    add_gemm_step(h, tn, idx, br[0].x, br[0].c, 64, 64, {{prev_last, prev_last_name, prev_last_c, 64, 64}});
+                    br[0].name = tn;
+                }                                          // else: the branch carries over unchanged (its x buffer already holds it)
+            } else {                                       // a new branch: one stride-2 3x3 conv from the previous stage's last branch
+                HMV_CHECK(i == nprev, "more than one new branch per stage");
+                const std::string k = t + "." + std::to_string(i) + ".0";
+                const int src_res = 64 >> prev_last_level;
+                HMV_CHECK(src_res == 2 * res_i, "transition must halve the resolution");
+                if (add_conv(h, tn, k + ".0", k + ".1", false, prev_last_c, br[i].c, 3, 2, src_res, src_res, prev_last, br[i].x, ACT_RELU, nullptr, &idx,
+                             prev_last_cp, br[i].cp)) return 1;
+                add_gemm_step(h, tn, idx, br[i].x, br[i].c, res_i, res_i, {{prev_last, prev_last_name, prev_last_c, src_res, src_res}});
+                br[i].name = tn;
+            }
+        }
+        for (int m = 0; m < nmod; ++m) {
+            const std::string p = "backbone.stage" + std::to_string(si + 2) + "." + std::to_string(m);
+            const std::string sp = "hr.stage" + std::to_string(si + 2) + "." + std::to_string(m);
+            // branches: 4 BasicBlocks each (hrnet.py:38-55)
+            for (int i = 0; i < nbr; ++i) {
+                const int res = 64 >> i;
+                for (int blk = 0; blk < 4; ++blk) {
+                    const std::string q = p + ".branches." + std::to_string(i) + "." + std::to_string(blk);
+                    const std::string qn = sp + ".b" + std::to_string(i) + "." + std::to_string(blk);
+                    if (add_conv(h, qn + ".conv1", q + ".conv1", q + ".bn1", false, br[i].c, br[i].c, 3, 1, res, res, br[i].x, br[i].t, ACT_RELU, nullptr, &idx,
+                                 br[i].cp, br[i].cp)) return 1;
+                    add_gemm_step(h, qn + ".conv1", idx, br[i].t, br[i].c, res, res, {{br[i].x, br[i].name, br[i].c, res, res}});
+                    const std::string out_name = blk == 3 ? sp + ".branch" + std::to_string(i) : qn + ".conv2";
+                    if (add_conv(h, out_name, q + ".conv2", q + ".bn2", false, br[i].c, br[i].c, 3, 1, res, res, br[i].t, br[i].y, ACT_RELU, br[i].x, &idx,
+                                 br[i].cp, br[i].cp)) return 1;
+                    add_gemm_step(h, out_name, idx, br[i].y, br[i].c, res, res, {{br[i].t, qn + ".conv1", br[i].c, res, res}, {br[i].x, br[i].name, br[i].c, res, res}});
+                    std::swap(br[i].x, br[i].y);
+                    br[i].name = out_name;
+                }
+            }
+            // fusion (hrnet.py:177-211, 222-231)
+            for (int i = 0; i < nbr; ++i) {
+                const int res_i = 64 >> i;
+                const std::string on = sp + ".out" + std::to_string(i);
+                const bool has_up = i + 1 < nbr;
+                // up terms first (their temps are independent): conv1x1 + BN at the source resolution
+                std::vector<std::pair<const void*, int>> ups;
+                std::vector<StepIO> fuse_ins;
+                for (int j = i + 1; j < nbr; ++j) {
+                    const std::string f = p + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
+                    const std::string fn = sp + ".up" + std::to_string(i) + std::to_string(j);
+                    const int res_j = 64 >> j;
+                    if (add_conv(h, fn, f + ".0", f + ".1", false, br[j].c, br[i].c, 1, 1, res_j, res_j, br[j].x, up[i][j], ACT_NONE, nullptr, &idx,
+                                 br[j].cp, br[i].cp)) return 1;
+                    add_gemm_step(h, fn, idx, up[i][j], br[i].c, res_j, res_j, {{br[j].x, br[j].name, br[j].c, res_j, res_j}});
+                    ups.push_back({up[i][j], j - i});
+                    fuse_ins.push_back({up[i][j], fn, br[i].c, res_j, res_j});
+                }
+                // down chains: the last conv of every chain adds the running sum (starting from x_i) as its residual
+                const void* run = br[i].x; std::string run_name = br[i].name;
+                for (int j = 0; j < i; ++j) {
+                    const std::string f = p + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
+                    const void* src = br[j].x; std::string src_name = br[j].name;
+                    for (int k = 0; k < i - j; ++k) {
+                        const bool last = k == i - j - 1;
+                        const int rin = 64 >> (j + k), rout = rin / 2;
+                        const std::string fk = f + "." + std::to_string(k);
+                        const std::string fn = sp + ".down" + std::to_string(i) + std::to_string(j) + "." + std::to_string(k);
+                        if (!last) {
+                            if (add_conv(h, fn, fk + ".0", fk + ".1", false, br[j].c, br[j].c, 3, 2, rin, rin, src, br[j + k + 1].d, ACT_RELU, nullptr, &idx,
+                                         br[j].cp, br[j].cp)) return 1;
+                            add_gemm_step(h, fn, idx, br[j + k + 1].d, br[j].c, rout, rout, {{const_cast<void*>(src), src_name, br[j].c, rin, rin}});
+                            src = br[j + k + 1].d; src_name = fn;
+                        } else {
+                            // final term of the whole sum and nothing to upsample: ReLU here, straight into the fused output
+                            const bool finish = j == i - 1 && !has_up;
+                            void* dst = finish ? br[i].z : br[i].r;
+                            if (add_conv(h, finish ? on : fn, fk + ".0", fk + ".1", false, br[j].c, br[i].c, 3, 2, rin, rin, src, dst, finish ? ACT_RELU : ACT_NONE, run,
+                                         &idx, br[j].cp, br[i].cp)) return 1;
+                            add_gemm_step(h, finish ? on : fn, idx, dst, br[i].c, res_i, res_i,
+                                          {{const_cast<void*>(src), src_name, br[j].c, rin, rin}, {const_cast<void*>(run), run_name, br[i].c, res_i, res_i}});
+                            run = dst; run_name = finish ? on : fn;
+                        }
+                    }
+                }
+                if (has_up) {
+                    fuse_ins.insert(fuse_ins.begin(), StepIO{const_cast<void*>(run), run_name, br[i].c, res_i, res_i});
+                    add_fuse_step(h, on, run, ups, br[i].z, i, br[i].cp, br[i].c, true, fuse_ins);
+                }
+            }
+            for (int i = 0; i < nbr; ++i) { std::swap(br[i].x, br[i].z); br[i].name = sp + ".out" + std::to_string(i); }
+        }
+        nprev = nbr;
+        prev_last = br[nbr - 1].x; prev_last_name = br[nbr - 1].name; prev_last_c = br[nbr - 1].c; prev_last_cp = br[nbr - 1].cp; prev_last_level = nbr - 1;
+    }
+    for (int l = 0; l < 4; ++l) h->hr_lvl[l] = br[l].x;
+    h->featbuf = br[0].x;
+    for (auto& st : h->backbone) {                    // every activation with C channels lives in a buffer of cpad(C) channels
+        for (auto& io : st.ins) io.ld = cpad(io.C);
+        for (auto& io : st.outs) io.ld = cpad(io.C);
+    }
+    return 0;
+}
+
 static int build_heads(hmv_handle* h) {
     const int hw = h->hm * h->hm;
     const int rows_max = h->fcap * h->S;
@@ -867,6 +1098,34 @@ static int build_heads(hmv_handle* h) {
         return 1;
 
     const int lp_out = h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR;
+    if (h->hr) {
+        // ---- pose_net of the HRNet configs: Conv2d(c0, 21, 3, stride 2, padding 1) on level 0 (handmvnet.py:50-56) ----
+        std::vector<float> wf, bf;
+        if (fold_conv(h, "pose_net", "", true, kJoints, h->hr_c[0], 3, wf, bf)) return 1;
+        if (add_conv_raw(h, "pose_net", wf, bf, h->hr_c[0], kJoints, 3, 2, 64, 64, h->hr_lvl[0], h->hm_int, ACT_NONE, nullptr, &h->pose3, hw, h->hr_cp[0], 0)) return 1;
+        // ---- one SampleNet per level on gathered rows (nets.py:55-63; gather-then-conv identity of SURVEY appendix D) ----
+        for (int l = 0; l < 4; ++l) {
+            const std::string q = "sample_nets." + std::to_string(l);
+            const int c = h->hr_c[l], cp = h->hr_cp[l], co = c / 2;
+            const size_t rows = static_cast<size_t>(h->mb_img) * kJoints * 4;
+            if (dev_alloc(h, &h->hr_rows[l], rows * cp * e) || dev_alloc_t(h, &h->hr_wts[l], rows * sizeof(float))) return 1;
+            std::vector<float> wf2, bf2;
+            if (fold_conv(h, q + ".conv.0", q + ".conv.1", true, co, c, 1, wf2, bf2)) return 1;
+            std::vector<float> wpad(static_cast<size_t>(co) * cp, 0.f);
+            for (int r = 0; r < co; ++r) memcpy(&wpad[static_cast<size_t>(r) * cp], &wf2[static_cast<size_t>(r) * c], sizeof(float) * c);
+            Layer L;
+            L.name = q; L.kind = LK_FLAT; L.cin = cp; L.cout = co; L.K = cp;
+            L.max_units = static_cast<int>(rows); L.in = h->hr_rows[l];
+            L.bn = tc_pick_bn(co); L.n_alloc = (co + L.bn - 1) / L.bn * L.bn;
+            if (!h->bf16) L.n_alloc = (co + 3) / 4 * 4;
+            if (dev_alloc_t(h, &h->hr_g[l], rows * L.n_alloc * sizeof(float))) return 1;
+            L.ep = make_ep(h->hr_g[l], L.n_alloc, OUT_F32_ROWMAJOR, ACT_RELU);
+            if (finish_layer(h, L, wpad, bf2)) return 1;
+            if (h->bf16 && build_tc(h, L)) return 1;
+            h->hr_samp[l] = static_cast<int>(h->layers.size());
+            h->layers.push_back(L);
+        }
+    } else {
     // ---- pose_net (layers.py:318-334 via handmvnet.py:71) ----
     if (add_conv(h, "pose_net.0", "pose_net.0", "pose_net.1", true, 1024, 512, 1, 1, h->hm, h->hm, h->featbuf, h->bufT1, ACT_RELU, nullptr, &h->pose0)) return 1;
     {
@@ -888,6 +1147,7 @@ static int build_heads(hmv_handle* h) {
         if (h->bf16 && build_tc(h, L)) return 1;
         h->samp = static_cast<int>(h->layers.size());
         h->layers.push_back(L);
+    }
     }
     // ---- constants: positional table (layers.py:136-150) and Chebyshev basis (layers.py:405-445) ----
     {
@@ -1045,6 +1305,14 @@ static int run_backbone_t(hmv_handle* h, const float* x, int n_img, int num_step
             ++h->launches;
             if (stem_pool_launch(x, h->x_u8, h->norm, static_cast<const bf16*>(h->stem_w), h->stem_b, static_cast<bf16*>(st.out), n_img,
                                  h->num_sms, h->err_flag_dev, s)) return 1;
+        } else if (st.kind == SK_HR_STEM) {
+            ++h->launches;
+            if (hr_stem_launch<T>(x, h->x_u8, h->norm, h->hr_stem_w, h->stem_b, static_cast<T*>(st.out), n_img, h->img, s)) return 1;
+        } else if (st.kind == SK_FUSE_SUM) {
+            ++h->launches;
+            FuseSumParams fp = st.fuse;
+            fp.n_img = n_img;
+            if (fuse_sum_launch<T>(fp, s)) return 1;
         } else if (st.kind == SK_TAIL) {
             if (run_tail(h, st.layer, n_img, s)) return 1;
         } else if (st.kind == SK_SEAM) {
@@ -1063,7 +1331,7 @@ static int run_backbone(hmv_handle* h, const float* x, int n_img, int num_steps,
 }
 
 static int run_pose(hmv_handle* h, int n_img, float* heatmap_out, float* xy_scaled_out, cudaStream_t s) {
-    if (run_layer(h, h->layers[h->pose0], n_img, s)) return 1;
+    if (h->pose0 >= 0 && run_layer(h, h->layers[h->pose0], n_img, s)) return 1;     // (HRNet: pose_net is one 3x3 / stride-2 conv, handmvnet.py:50-56)
     float* hm = heatmap_out ? heatmap_out : h->hm_int;
     if (run_layer(h, h->layers[h->pose3], n_img, s, hm)) return 1;
     ++h->launches;
@@ -1074,11 +1342,35 @@ static int run_pose(hmv_handle* h, int n_img, float* heatmap_out, float* xy_scal
 // tokens of this micro-batch are written at sample offset `off` of the (fusion-pass wide) token stream
 template <typename T>
 static int run_sample_t(hmv_handle* h, int n_img, const float* bbox, const float* intr, cudaStream_t s, int off = 0) {
+    if (h->hr) {
+        // one SampleNet per level (handmvnet.py:97,185): the joint coordinates address every level with the SAME un-rescaled
+        // heat-map pixel numbers (nets.py:46-53 normalises by the level's own size) - reproduced by sample_gather_kernel
+        TokenParams tp{};
+        tp.n_src = 4;
+        for (int l = 0; l < 4; ++l) {
+            const int res = 64 >> l;
+            h->launches += 1;
+            if (sample_gather_launch<T>(static_cast<const T*>(h->hr_lvl[l]), h->xy, static_cast<T*>(h->hr_rows[l]), h->hr_wts[l], n_img, res, res, h->hr_cp[l], s)) return 1;
+            const Layer& L = h->layers[h->hr_samp[l]];
+            if (run_layer(h, h->layers[h->hr_samp[l]], n_img * kJoints * 4, s)) return 1;
+            tp.src[l] = TokenSource{h->hr_g[l], h->hr_wts[l], L.ep.ldc, h->hr_c[l] / 2};
+        }
+        tp.xy = h->xy;
+        tp.bbox = bbox; tp.intr = intr; tp.pe = h->cfg.use_sin ? h->pe : nullptr;
+        const size_t tok_off = static_cast<size_t>(off) * h->S * h->pitch;
+        tp.tok_f32 = h->tok0_f32 + tok_off; tp.tok_lp = static_cast<T*>(h->tok0_lp) + tok_off;
+        tp.n_img = n_img; tp.feat = h->feat; tp.d = h->d; tp.pitch = h->pitch; tp.tokens_per_sample = h->S;
+        tp.use_pos2d = h->cfg.use_pos2d; tp.use_crop = h->cfg.use_crop;
+        ++h->launches;
+        return tokens_launch<T>(tp, s);
+    }
     h->launches += 2;
     if (sample_gather_launch<T>(static_cast<const T*>(h->featbuf), h->xy, static_cast<T*>(h->bufT2), h->wts, n_img, h->hm, h->hm, 1024, s)) return 1;
     if (run_layer(h, h->layers[h->samp], n_img * kJoints * 4, s)) return 1;
     TokenParams tp{};
-    tp.g = static_cast<const float*>(h->bufDS); tp.ldg = 512; tp.wts = h->wts; tp.xy = h->xy;
+    tp.n_src = 1;
+    tp.src[0] = TokenSource{static_cast<const float*>(h->bufDS), h->wts, 512, h->feat};
+    tp.xy = h->xy;
     tp.bbox = bbox; tp.intr = intr; tp.pe = h->cfg.use_sin ? h->pe : nullptr;
     const size_t tok_off = static_cast<size_t>(off) * h->S * h->pitch;
     tp.tok_f32 = h->tok0_f32 + tok_off; tp.tok_lp = static_cast<T*>(h->tok0_lp) + tok_off;
@@ -1196,6 +1488,7 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     HMV_CHECK(cfg->image_size == 256 && cfg->heatmap_size == 32, "only image_size 256 / heatmap_size 32 (release configs) are supported");
     HMV_CHECK(cfg->micro_batch >= 1, "micro_batch must be >= 1");
     HMV_CHECK(cfg->precision == HMV_PRECISION_BF16 || cfg->precision == HMV_PRECISION_FP32, "unknown precision");
+    HMV_CHECK(cfg->backbone == HMV_BACKBONE_RESNET50_PAPER || cfg->backbone == HMV_BACKBONE_HRNET, "unknown backbone");
     int ndev = 0;
     HMV_CUDA(cudaGetDeviceCount(&ndev));
     HMV_CHECK(ndev > 0, "no CUDA device: handmvnet_b200 has no CPU fallback");
@@ -1210,8 +1503,21 @@ int hmv_create(const hmv_config* cfg, hmv_handle** out) {
     h->esz = h->bf16 ? 2 : 4;
     h->V = cfg->num_views; h->S = 21 * cfg->num_views;
     h->img = cfg->image_size; h->hm = cfg->heatmap_size;
+    h->hr = cfg->backbone == HMV_BACKBONE_HRNET;
+    if (h->hr) {                                     // feat_dim = sum(backbone_channels) / 2 (handmvnet.py:88)
+        int sum = 0;
+        for (int l = 0; l < 4; ++l) {
+            h->hr_c[l] = cfg->hr_channels[l];
+            if (h->hr_c[l] < 8 || h->hr_c[l] % 8 != 0 || h->hr_c[l] > 512) { hmv::set_error("hr_channels must be multiples of 8 in [8, 512]"); delete h; return 1; }
+            const int c = h->hr_c[l];
+            h->hr_cp[l] = !h->bf16 ? c : (c <= 64 ? 64 : c <= 128 ? 128 : c <= 192 ? 192 : (c + 63) / 64 * 64);
+            sum += c;
+        }
+        h->feat = sum / 2;
+    }
     h->d = h->feat + (cfg->use_pos2d ? 2 : 0) + (cfg->use_crop ? 10 : 0);
     h->pitch = (h->d + 63) / 64 * 64;
+    if (h->pitch > 256 && h->pitch % 128 != 0 && h->pitch < (h->d + 175) / 176 * 176) h->pitch = ((h->d + 175) / 176 * 176 + 63) / 64 * 64;   // to_out tile width (176) must fit the token pitch
     h->mb = cfg->micro_batch; h->mb_img = h->mb * h->V;
     h->fcap = h->mb >= 256 ? h->mb : (256 / h->mb) * h->mb;          // a multiple of the micro-batch
     h->num_sms = prop.multiProcessorCount;
@@ -1287,7 +1593,7 @@ int hmv_prepare(hmv_handle* h) {
     HMV_CHECK(h, "hmv_prepare: null handle");
     HMV_CHECK(!h->prepared, "hmv_prepare called twice");
     hmv::DeviceGuard guard(h->cfg.device);
-    if (hmv::build_backbone(h)) return 1;
+    if (h->hr ? hmv::build_hrnet(h) : hmv::build_backbone(h)) return 1;
     if (hmv::build_heads(h)) return 1;
     {   // small-batch CUDA-graph path (HMV_NO_GRAPH=1 disables it)
         const char* e = getenv("HMV_NO_GRAPH");
@@ -1675,10 +1981,14 @@ int hmv_tensor_get(hmv_handle* h, int32_t tensor, float* dst, int32_t batch, voi
     const int n_img = batch * h->V, hw = h->hm * h->hm;
     if (batch == 0) return 0;
     switch (tensor) {
-        case HMV_T_FEAT: {
-            const size_t total = static_cast<size_t>(n_img) * 1024 * hw;
-            if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(h->featbuf), dst, 1024, hw, total);
-            else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(h->featbuf), dst, 1024, hw, total);
+        case HMV_T_FEAT: case HMV_T_FEAT1: case HMV_T_FEAT2: case HMV_T_FEAT3: {
+            const int l = tensor == HMV_T_FEAT ? 0 : tensor - HMV_T_FEAT1 + 1;
+            HMV_CHECK(h->hr || l == 0, "feature levels 1..3 exist for the HRNet backbone only");
+            const int C = h->hr ? h->hr_c[l] : 1024, ld = h->hr ? h->hr_cp[l] : 1024, px = h->hr ? (64 >> l) * (64 >> l) : hw;
+            const void* src = h->hr ? h->hr_lvl[l] : h->featbuf;
+            const size_t total = static_cast<size_t>(n_img) * C * px;
+            if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(src), dst, C, px, total, ld);
+            else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(src), dst, C, px, total, ld);
             break;
         }
         case HMV_T_HEATMAP:
@@ -1715,10 +2025,14 @@ int hmv_tensor_set(hmv_handle* h, int32_t tensor, const float* src, int32_t batc
     const int n_img = batch * h->V, hw = h->hm * h->hm;
     if (batch == 0) return 0;
     switch (tensor) {
-        case HMV_T_FEAT: {
-            const size_t total = static_cast<size_t>(n_img) * 1024 * hw;
-            if (h->bf16) hmv::nchw_to_nhwc_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(src, static_cast<hmv::bf16*>(h->featbuf), 1024, hw, total);
-            else hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(src, static_cast<float*>(h->featbuf), 1024, hw, total);
+        case HMV_T_FEAT: case HMV_T_FEAT1: case HMV_T_FEAT2: case HMV_T_FEAT3: {
+            const int l = tensor == HMV_T_FEAT ? 0 : tensor - HMV_T_FEAT1 + 1;
+            HMV_CHECK(h->hr || l == 0, "feature levels 1..3 exist for the HRNet backbone only");
+            const int C = h->hr ? h->hr_c[l] : 1024, ld = h->hr ? h->hr_cp[l] : 1024, px = h->hr ? (64 >> l) * (64 >> l) : hw;
+            void* dstb = h->hr ? h->hr_lvl[l] : h->featbuf;
+            const size_t total = static_cast<size_t>(n_img) * ld * px;
+            if (h->bf16) hmv::nchw_to_nhwc_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(src, static_cast<hmv::bf16*>(dstb), C, px, total, ld);
+            else hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(src, static_cast<float*>(dstb), C, px, total, ld);
             break;
         }
         case HMV_T_HEATMAP:
@@ -1762,8 +2076,9 @@ int hmv_debug_backbone(hmv_handle* h, const float* x, int32_t n_img, int32_t num
     const hmv::Step& st = h->backbone[num_steps - 1];
     chw[0] = st.C; chw[1] = st.H; chw[2] = st.W;
     const size_t total = static_cast<size_t>(n_img) * st.C * st.H * st.W;
-    if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(st.out), out, st.C, st.H * st.W, total);
-    else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(st.out), out, st.C, st.H * st.W, total);
+    const int ld = st.outs.empty() ? 0 : st.outs[0].ld;
+    if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(st.out), out, st.C, st.H * st.W, total, ld);
+    else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(st.out), out, st.C, st.H * st.W, total, ld);
     HMV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1792,9 +2107,10 @@ int hmv_debug_step_run(hmv_handle* h, int32_t step, int32_t n_img, const float* 
     for (size_t i = 0; i < st.ins.size(); ++i) {
         const hmv::StepIO& io = st.ins[i];
         HMV_CHECK(inputs[i], "hmv_debug_step_run: null input");
-        const size_t total = static_cast<size_t>(n_img) * io.C * io.H * io.W;
-        if (h->bf16) hmv::nchw_to_nhwc_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<hmv::bf16*>(io.ptr), io.C, io.H * io.W, total);
-        else hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<float*>(io.ptr), io.C, io.H * io.W, total);
+        const int ld = io.ld ? io.ld : io.C;
+        const size_t total = static_cast<size_t>(n_img) * ld * io.H * io.W;
+        if (h->bf16) hmv::nchw_to_nhwc_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<hmv::bf16*>(io.ptr), io.C, io.H * io.W, total, ld);
+        else hmv::nchw_to_nhwc_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(inputs[i], static_cast<float*>(io.ptr), io.C, io.H * io.W, total, ld);
     }
     HMV_CUDA(cudaGetLastError());
     int rc = 1;
@@ -1805,6 +2121,11 @@ int hmv_debug_step_run(hmv_handle* h, int32_t step, int32_t n_img, const float* 
         ++h->launches;
         rc = h->bf16 ? hmv::maxpool_launch<hmv::bf16>(static_cast<const hmv::bf16*>(st.in), static_cast<hmv::bf16*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s)
                      : hmv::maxpool_launch<float>(static_cast<const float*>(st.in), static_cast<float*>(st.out), n_img, st.H * 2, st.W * 2, st.C, s);
+    } else if (st.kind == hmv::SK_FUSE_SUM) {
+        ++h->launches;
+        hmv::FuseSumParams fp = st.fuse;
+        fp.n_img = n_img;
+        rc = h->bf16 ? hmv::fuse_sum_launch<hmv::bf16>(fp, s) : hmv::fuse_sum_launch<float>(fp, s);
     } else {
         hmv::set_error("hmv_debug_step_run: unsupported step kind");
     }
@@ -1813,8 +2134,8 @@ int hmv_debug_step_run(hmv_handle* h, int32_t step, int32_t n_img, const float* 
         const hmv::StepIO& io = st.outs[i];
         HMV_CHECK(outputs[i], "hmv_debug_step_run: null output");
         const size_t total = static_cast<size_t>(n_img) * io.C * io.H * io.W;
-        if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(io.ptr), outputs[i], io.C, io.H * io.W, total);
-        else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(io.ptr), outputs[i], io.C, io.H * io.W, total);
+        if (h->bf16) hmv::nhwc_to_nchw_kernel<hmv::bf16><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const hmv::bf16*>(io.ptr), outputs[i], io.C, io.H * io.W, total, io.ld);
+        else hmv::nhwc_to_nchw_kernel<float><<<hmv::nblk(total), 256, 0, s>>>(static_cast<const float*>(io.ptr), outputs[i], io.C, io.H * io.W, total, io.ld);
     }
     HMV_CUDA(cudaGetLastError());
     return hmv::ws_release(h, s);

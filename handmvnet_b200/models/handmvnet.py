@@ -71,6 +71,86 @@ class _ResNet50Paper(_NoEagerPath):
         return nn.Sequential(*layers)
 
 
+class _BasicBlock(_NoEagerPath):
+    """Parameters of reference backbones/hrnet.py:26-36."""
+
+    def __init__(self, planes):
+        super().__init__()
+        self.conv1 = nn.Conv2d(planes, planes, kernel_size=3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+
+
+def _conv_bn(cin, cout, k, stride=1, relu=False):
+    layers = [nn.Conv2d(cin, cout, k, stride, k // 2, bias=False), nn.BatchNorm2d(cout)]
+    if relu:
+        layers.append(nn.ReLU(False))
+    return nn.Sequential(*layers)
+
+
+class _HRModule(_NoEagerPath):
+    """Parameters of reference hrnet.py:97-211 (HighResolutionModule: 4 BasicBlocks per branch + fuse layers)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        n = len(channels)
+        self.branches = nn.ModuleList([nn.Sequential(*[_BasicBlock(c) for _ in range(4)]) for c in channels])
+        fuse = []
+        for i in range(n):
+            row = []
+            for j in range(n):
+                if j > i:
+                    row.append(nn.Sequential(nn.Conv2d(channels[j], channels[i], 1, 1, 0, bias=False), nn.BatchNorm2d(channels[i]),
+                                             nn.Upsample(scale_factor=2 ** (j - i), mode="nearest")))
+                elif j == i:
+                    row.append(None)
+                else:
+                    row.append(nn.Sequential(*[_conv_bn(channels[j], channels[i] if k == i - j - 1 else channels[j], 3, 2, relu=k < i - j - 1)
+                                               for k in range(i - j)]))
+            fuse.append(nn.ModuleList(row))
+        self.fuse_layers = nn.ModuleList(fuse)
+
+
+HR_CHANNELS = {"w40": (40, 80, 160, 320), "w64": (64, 128, 256, 512)}
+
+
+class _HRNet(_NoEagerPath):
+    """Parameters of reference HRNet (backbones/hrnet.py:241-276, 427-495): 3x3/2 stem x2, 4 Bottlenecks, stages 2-4 with
+    1 / 4 / 3 modules of 2 / 3 / 4 branches; kaiming_normal(fan_out) convs, unit BatchNorm (hrnet.py:412-418)."""
+
+    def __init__(self, hrnet_type="w40"):
+        super().__init__()
+        if hrnet_type not in HR_CHANNELS:
+            raise Exception("HRNet only supports ['w64', 'w40'] as model_type, found: " + hrnet_type)
+        ch = HR_CHANNELS[hrnet_type]
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=3, stride=2, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.conv2 = nn.Conv2d(64, 64, kernel_size=3, stride=2, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(64)
+        ds = nn.Sequential(nn.Conv2d(64, 256, kernel_size=1, bias=False), nn.BatchNorm2d(256))
+        self.layer1 = nn.Sequential(_Bottleneck(64, 64, 1, ds), *[_Bottleneck(256, 64) for _ in range(3)])
+        pre = [256]
+        for si, (nmod, nbr) in enumerate(((1, 2), (4, 3), (3, 4)), start=2):
+            cur = list(ch[:nbr])
+            trans = []
+            for i in range(nbr):
+                if i < len(pre):
+                    trans.append(_conv_bn(pre[i], cur[i], 3, 1, relu=True) if cur[i] != pre[i] else None)
+                else:
+                    trans.append(nn.Sequential(*[_conv_bn(pre[-1], cur[i] if j == i - len(pre) else pre[-1], 3, 2, relu=True)
+                                                 for j in range(i + 1 - len(pre))]))
+            setattr(self, f"transition{si - 1}", nn.ModuleList(trans))
+            setattr(self, f"stage{si}", nn.Sequential(*[_HRModule(cur) for _ in range(nmod)]))
+            pre = cur
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
 class _SampleNet(_NoEagerPath):
     """Parameters of reference nets.py:24-31 (SampleNet([c, c//2]))."""
 
@@ -199,21 +279,28 @@ class HandMvNet(nn.Module):
 
         self.backbone_name = model_params.get("backbone", "hrnet")
         assert self.backbone_name in ["hrnet", "resnet"], "Backbone should be one of ['hrnet', 'resnet']"
-        if self.backbone_name == "hrnet":
-            raise NotImplementedError("HRNet backbones are outside the B200 hot path (SURVEY.md §8f rank 3)")
-        self.backbone_type = model_params.get("backbone_type", "34")
-        assert self.backbone_type in ["18", "34", "50_paper"], "Supports only 18, 34, 50_paper"
-        if self.backbone_type != "50_paper":
-            raise NotImplementedError("only backbone_type '50_paper' (the release ResNet configs) is built")
-        self.backbone_channels = model_params["backbone_channels"]
-        if list(self.backbone_channels) != [1024]:
-            raise NotImplementedError("backbone_channels must be [1024] for the 50_paper backbone")
         if data_params.get("image_size", 256) != 256 or data_params.get("heatmap_size", 32) != 32:
             raise NotImplementedError("only image_size 256 / heatmap_size 32 (all release configs) are built")
-        # weights pretrained on ImageNet cannot be fetched offline; a checkpoint is loaded with load_state_dict
-        self.backbone = _ResNet50Paper()
-        self.pose_net = nn.Sequential(nn.Conv2d(1024, 512, kernel_size=1), nn.BatchNorm2d(512), nn.ReLU(inplace=True),
-                                      nn.Conv2d(512, NUM_JOINTS, kernel_size=1))
+        if self.backbone_name == "hrnet":
+            # the `*_HR*` release configs (reference handmvnet.py:41-56): HRNet-w40 / w64, four feature levels
+            self.backbone_type = model_params.get("backbone_type", "w40")
+            self.backbone_channels = model_params["backbone_channels"]
+            self.backbone = _HRNet(self.backbone_type)
+            if tuple(self.backbone_channels) != HR_CHANNELS[self.backbone_type]:
+                raise ValueError(f"backbone_channels {list(self.backbone_channels)} do not match HRNet-{self.backbone_type}")
+            self.pose_net = nn.Conv2d(self.backbone_channels[0], NUM_JOINTS, kernel_size=3, stride=2, padding=1)
+        else:
+            self.backbone_type = model_params.get("backbone_type", "34")
+            assert self.backbone_type in ["18", "34", "50_paper"], "Supports only 18, 34, 50_paper"
+            if self.backbone_type != "50_paper":
+                raise NotImplementedError("only backbone_type '50_paper' (the release ResNet configs) is built")
+            self.backbone_channels = model_params["backbone_channels"]
+            if list(self.backbone_channels) != [1024]:
+                raise NotImplementedError("backbone_channels must be [1024] for the 50_paper backbone")
+            # weights pretrained on ImageNet cannot be fetched offline; a checkpoint is loaded with load_state_dict
+            self.backbone = _ResNet50Paper()
+            self.pose_net = nn.Sequential(nn.Conv2d(1024, 512, kernel_size=1), nn.BatchNorm2d(512), nn.ReLU(inplace=True),
+                                          nn.Conv2d(512, NUM_JOINTS, kernel_size=1))
 
         self.feat_dim = int(sum(self.backbone_channels) / 2)
         self.pos_enc_list = model_params.get("pos_enc", ["pos2d", "sin"])
@@ -303,7 +390,10 @@ class HandMvNet(nn.Module):
                              heatmap_size=self.data_params.get("heatmap_size", 32),
                              use_pos2d=int("pos2d" in self.pos_enc_list), use_crop=int("crop" in self.pos_enc_list),
                              use_sin=int(self.sinusoidal_pos), fusion_layers=self.fusion_layers,
-                             precision=_lib.PRECISION[self.precision], micro_batch=self.micro_batch, device=index)
+                             precision=_lib.PRECISION[self.precision], micro_batch=self.micro_batch, device=index,
+                             backbone=_lib.BACKBONE[self.backbone_name])
+        if self.backbone_name == "hrnet":
+            cfg.hr_channels = (ctypes.c_int32 * 4)(*self.backbone_channels)
         handle = ctypes.c_void_p()
         with torch.cuda.device(index):
             _lib.check(lib.hmv_create(ctypes.byref(cfg), ctypes.byref(handle)), "hmv_create")
@@ -500,6 +590,12 @@ class HandMvNet(nn.Module):
 
     def _tensor_shape(self, name, batch):
         v, d = self.num_views, self.feat_dim
+        if self.backbone_name == "hrnet":
+            c = self.backbone_channels
+            lv = {"feat": (batch * v, c[0], 64, 64), "feat1": (batch * v, c[1], 32, 32), "feat2": (batch * v, c[2], 16, 16),
+                  "feat3": (batch * v, c[3], 8, 8)}
+            if name in lv:
+                return lv[name]
         return {"feat": (batch * v, 1024, 32, 32), "heatmap": (batch * v, NUM_JOINTS, 32, 32),
                 "xy": (batch * v, NUM_JOINTS, 2), "tokens": (batch, NUM_JOINTS * v, d),
                 "fused": (batch, NUM_JOINTS, d), "joints": (batch, NUM_JOINTS, 3)}[name]

@@ -36,7 +36,10 @@ typedef struct hmv_config {
     int32_t precision;        /* HMV_PRECISION_BF16 (tcgen05 path) | HMV_PRECISION_FP32 (check mode) */
     int32_t micro_batch;      /* samples processed per internal pass (workspace is sized for it) */
     int32_t device;           /* CUDA device ordinal                                */
+    int32_t backbone;         /* model.backbone: HMV_BACKBONE_RESNET50_PAPER (0, default) | HMV_BACKBONE_HRNET */
+    int32_t hr_channels[4];   /* model.backbone_channels of the HRNet configs (w40: 40, 80, 160, 320)          */
 } hmv_config;
+enum { HMV_BACKBONE_RESNET50_PAPER = 0, HMV_BACKBONE_HRNET = 1 };
 
 /* HandMvNet(train_params, model_params, data_params)  - src/models/handmvnet.py:28 */
 int hmv_create(const hmv_config* cfg, hmv_handle** out);
@@ -108,12 +111,15 @@ enum {
     HMV_STAGE_SOFTARGMAX = 5  /* models/utils.py:35-62   HEATMAP -> XY (soft_argmax_2d alone) */
 };
 enum {
-    HMV_T_FEAT = 0,           /* [n*V, 1024, 32, 32] NCHW                                    */
+    HMV_T_FEAT = 0,           /* [n*V, 1024, 32, 32] NCHW (HRNet: level 0, [n*V, C_0, 64, 64])  */
     HMV_T_HEATMAP = 1,        /* [n*V, 21, 32, 32]                                          */
     HMV_T_XY = 2,             /* [n*V, 21, 2] heatmap pixels                                 */
     HMV_T_TOKENS = 3,         /* [n, 21*V, feat_dim] (positional encoding already added)     */
     HMV_T_FUSED = 4,          /* [n, 21, feat_dim]                                           */
-    HMV_T_JOINTS = 5          /* [n, 21, 3]                                                  */
+    HMV_T_JOINTS = 5,         /* [n, 21, 3]                                                  */
+    HMV_T_FEAT1 = 6,          /* HRNet only: feature levels 1..3, [n*V, C_l, 64 >> l, 64 >> l] (HMV_T_FEAT is level 0 there) */
+    HMV_T_FEAT2 = 7,
+    HMV_T_FEAT3 = 8
 };
 /* Runs one stage on the handle's internal tensors for `batch` <= micro_batch samples.
  * x / bbox / intr are only read by the stages that need them (others may pass NULL). */

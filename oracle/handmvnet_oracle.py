@@ -314,11 +314,16 @@ def _conv_bn(sd, conv, bn, x, stride=1, relu=True):
     return F.relu(y) if relu else y
 
 
-def basic_block(sd, p, x):
+def basic_block(sd, p, x, taps=None, key=None):
     """reference hrnet.py:38-55 (BasicBlock.forward, no downsample in HRNet branches)."""
     out = _conv_bn(sd, p + ".conv1", p + ".bn1", x)
+    if taps is not None:
+        taps[key + ".conv1"] = out
     out = _conv_bn(sd, p + ".conv2", p + ".bn2", out, relu=False)
-    return F.relu(out + x)
+    out = F.relu(out + x)
+    if taps is not None:
+        taps[key + ".conv2"] = out
+    return out
 
 
 def hr_module(sd, p, xs, taps=None, key=None):
@@ -329,7 +334,7 @@ def hr_module(sd, p, xs, taps=None, key=None):
     xs = list(xs)
     for i in range(nbr):
         for blk in range(4):
-            xs[i] = basic_block(sd, f"{p}.branches.{i}.{blk}", xs[i])
+            xs[i] = basic_block(sd, f"{p}.branches.{i}.{blk}", xs[i], taps, f"{key}.b{i}.{blk}")
         if taps is not None:
             taps[f"{key}.branch{i}"] = xs[i]
     outs = []
@@ -341,11 +346,15 @@ def hr_module(sd, p, xs, taps=None, key=None):
                 t = xs[j]
             elif j > i:
                 t = _conv_bn(sd, f + ".0", f + ".1", xs[j], relu=False)
+                if taps is not None:
+                    taps[f"{key}.up{i}{j}"] = t
                 t = F.interpolate(t, scale_factor=2 ** (j - i), mode="nearest")
             else:
                 t = xs[j]
                 for k in range(i - j):
                     t = _conv_bn(sd, f"{f}.{k}.0", f"{f}.{k}.1", t, stride=2, relu=k < i - j - 1)
+                    if taps is not None and k < i - j - 1:
+                        taps[f"{key}.down{i}{j}.{k}"] = t
             y = t if y is None else y + t
         outs.append(F.relu(y))
         if taps is not None:
@@ -363,7 +372,10 @@ def hrnet_backbone(sd, x, taps=None):
     if taps is not None:
         taps["hr.conv2"] = x
     for b in range(4):
-        x = bottleneck(sd, f"backbone.layer1.{b}", x, 1)
+        blk_taps = {} if taps is not None else None
+        x = bottleneck(sd, f"backbone.layer1.{b}", x, 1, blk_taps)
+        if taps is not None:
+            taps.update({"hr." + k: v for k, v in blk_taps.items()})
     if taps is not None:
         taps["hr.layer1"] = x
     ys = [x]

@@ -14,10 +14,10 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def build_pair(views=5, crop=True, precision="bf16", micro_batch=2, seed=0, randomize_norm=True):
+def build_pair(views=5, crop=True, precision="bf16", micro_batch=2, seed=0, randomize_norm=True, backbone="resnet"):
     """(product model on cuda:0, oracle cfg, state_dict) sharing identical weights."""
-    cfg = release_config(views, crop)
-    ocfg = O.release_config(views, crop)
+    cfg = release_config(views, crop, backbone=backbone)
+    ocfg = O.release_config(views, crop, backbone)
     sd = O.make_state_dict(ocfg, seed=seed, randomize_norm=randomize_norm)
     m = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision=precision, micro_batch=micro_batch)
     m.load_state_dict(sd, strict=True)

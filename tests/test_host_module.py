@@ -51,8 +51,22 @@ def test_constructor_error_conventions():
         HandMvNet(cfg["train"], dict(cfg["model"], fusion_layers=4), cfg["data"])
     with pytest.raises(NotImplementedError):       # scoped out
         HandMvNet(dict(cfg["train"], root_relative=False), cfg["model"], cfg["data"])
-    with pytest.raises(NotImplementedError):
-        HandMvNet(cfg["train"], dict(cfg["model"], backbone="hrnet"), cfg["data"])
+    with pytest.raises(ValueError):                # HRNet widths must match the type (w40: 40/80/160/320)
+        HandMvNet(cfg["train"], dict(cfg["model"], backbone="hrnet", backbone_type="w40", backbone_channels=[1024]), cfg["data"])
+    with pytest.raises(Exception, match="HRNet only supports"):    # backbones/hrnet.py:444
+        HandMvNet(cfg["train"], dict(cfg["model"], backbone="hrnet", backbone_type="w18", backbone_channels=[18, 36, 72, 144]), cfg["data"])
+
+
+@pytest.mark.parametrize("views,crop", [(5, True), (4, False)])
+def test_state_dict_contract_hrnet(views, crop):
+    """The `*_HR*` release configs: 1941 keys in the reference's order, strict load of a reference-shaped state_dict."""
+    cfg = release_config(views, crop, backbone="hrnet")
+    m = HandMvNet(cfg["train"], cfg["model"], cfg["data"])
+    ocfg = O.release_config(views, crop, "hrnet")
+    spec = [(k, tuple(s)) for k, s, _ in O._state_dict_spec(ocfg)]
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec and len(spec) == 1941
+    assert m.feat_dim == (312 if crop else 302)
+    m.load_state_dict(O.make_state_dict(ocfg, seed=3), strict=True)
 
 
 def test_no_cpu_fallback_and_input_validation():
