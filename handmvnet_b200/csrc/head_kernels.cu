@@ -127,7 +127,11 @@ __global__ void softargmax_kernel(const float* __restrict__ hm, float* __restric
     float mx = -INFINITY;
     for (int i = lane; i < nvec; i += 32) {
         const float4 q = __ldg(p + i);
-        mx = fmaxf(mx, fmaxf(fmaxf(q.x * temperature, q.y * temperature), fmaxf(q.z * temperature, q.w * temperature)));
+        // __fmul_rn: the product must be ROUNDED exactly as in the second pass (an FMA-contracted `v * T - mx` keeps the
+        // exact product and leaves a residual of up to half an ulp of mx - thousands when the heat-map is ~1e8 as with
+        // random-init HRNet weights - in the exponent of the maximum element: exp -> inf -> NaN)
+        mx = fmaxf(mx, fmaxf(fmaxf(__fmul_rn(q.x, temperature), __fmul_rn(q.y, temperature)),
+                             fmaxf(__fmul_rn(q.z, temperature), __fmul_rn(q.w, temperature))));
     }
     mx = warp_max(mx);
     float se = 0.f, sx = 0.f, sy = 0.f;
@@ -137,7 +141,7 @@ __global__ void softargmax_kernel(const float* __restrict__ hm, float* __restric
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = i * 4 + k;
-            const float e = expf(v[k] * temperature - mx);
+            const float e = expf(__fsub_rn(__fmul_rn(v[k], temperature), mx));
             se += e;
             sx += e * static_cast<float>(idx % W);
             sy += e * static_cast<float>(idx / W);

@@ -1116,7 +1116,10 @@ static int build_heads(hmv_handle* h) {
             Layer L;
             L.name = q; L.kind = LK_FLAT; L.cin = cp; L.cout = co; L.K = cp;
             L.max_units = static_cast<int>(rows); L.in = h->hr_rows[l];
-            L.bn = tc_pick_bn(co); L.n_alloc = (co + L.bn - 1) / L.bn * L.bn;
+            L.bn = tc_pick_bn(co);
+            if (L.bn == 0) L.bn = tc_pick_bn((co + 191) / 192 * 192);
+            HMV_CHECK(L.bn > 0, "no tile width for " + q);
+            L.n_alloc = (co + L.bn - 1) / L.bn * L.bn;
             if (!h->bf16) L.n_alloc = (co + 3) / 4 * 4;
             if (dev_alloc_t(h, &h->hr_g[l], rows * L.n_alloc * sizeof(float))) return 1;
             L.ep = make_ep(h->hr_g[l], L.n_alloc, OUT_F32_ROWMAJOR, ACT_RELU);

@@ -231,6 +231,11 @@ def make_state_dict(cfg: dict, seed: int = 0, randomize_norm: bool = True) -> "O
             t = torch.randn(shape, generator=g) * 1e-3 if randomize_norm else torch.zeros(shape)
         elif kind in ("bn_gamma", "ln_gamma"):        # U(0.75, 1.25): visible in a wrong fold, yet well conditioned
             t = torch.rand(shape, generator=g) * 0.5 + 0.75 if randomize_norm else torch.ones(shape)
+            if randomize_norm and ".branches." in key and key.endswith(".bn2.weight"):
+                # HRNet: 32 residual BasicBlocks in a row double the activation variance each with unit gammas (1e8-1e9 at
+                # the outputs: every softmax downstream degenerates into a hard max); a small last-BN gain per block - what
+                # trained residual nets converge to - keeps the synthetic checkpoint O(1) and the comparison meaningful
+                t = t * 0.3
         elif kind in ("bn_beta", "ln_beta", "bn_mean"):
             t = torch.randn(shape, generator=g) * 0.1 if randomize_norm else torch.zeros(shape)
         elif kind == "bn_var":
