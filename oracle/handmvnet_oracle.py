@@ -234,8 +234,10 @@ def make_state_dict(cfg: dict, seed: int = 0, randomize_norm: bool = True) -> "O
             if randomize_norm and ".branches." in key and key.endswith(".bn2.weight"):
                 # HRNet: 32 residual BasicBlocks in a row double the activation variance each with unit gammas (1e8-1e9 at
                 # the outputs: every softmax downstream degenerates into a hard max); a small last-BN gain per block - what
-                # trained residual nets converge to - keeps the synthetic checkpoint O(1) and the comparison meaningful
-                t = t * 0.3
+                # trained residual nets converge to - keeps the synthetic checkpoint O(10) and the comparison meaningful
+                t = t * 0.15
+            if randomize_norm and ".fuse_layers." in key and key.endswith(".1.weight"):
+                t = t * 0.5                          # same for the 2-4 terms every fusion sum adds up, 8 modules deep
         elif kind in ("bn_beta", "ln_beta", "bn_mean"):
             t = torch.randn(shape, generator=g) * 0.1 if randomize_norm else torch.zeros(shape)
         elif kind == "bn_var":
