@@ -38,6 +38,7 @@ METRIC_FMT = "multi-view hand poses/sec (HandMvNet forward, release config, {v} 
 UNIT = "poses/s"
 FLOP_PER_SAMPLE_V5 = 108.515e9        # SURVEY.md §8d (FlopCounterMode over the reference forward)
 FLOP_PER_SAMPLE = {5: 108.515e9, 8: 173.58e9}
+FLOP_PER_SAMPLE_HRNET = {5: 153.26e9}   # FlopCounterMode over the oracle's HO3D_HandMvNet_HR forward (HRNet-w40, 52.8 M parameters)
 
 
 def load_peaks():
@@ -181,7 +182,7 @@ def run_own(args, lines):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     views, B = args.views, args.batch
-    cfg = release_config(views, True)
+    cfg = release_config(views, True, backbone=args.backbone)
     torch.manual_seed(0)
     model = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision="bf16", micro_batch=args.micro_batch)
     model.to(dev).eval()
@@ -317,12 +318,13 @@ def run_own(args, lines):
         value = B * world * args.steps / (dev_ms * 1e-3)
         step_ms_mean = dev_ms / args.steps
         line = {
-            "metric": METRIC if views == 5 else METRIC_FMT.format(v=views), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": (METRIC if views == 5 else METRIC_FMT.format(v=views)) + (" [HRNet-w40 backbone]" if args.backbone == "hrnet" else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms_mean,
             "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{'HO3D' if views == 5 else 'DexYCB-style'}_HandMvNet release config, synthetic {views}-view B={B} per GPU, bf16, random-init weights",
+            "config": {"workload": f"{'HO3D' if views == 5 else 'DexYCB-style'}_HandMvNet{'_HR' if args.backbone == 'hrnet' else ''} release config, synthetic {views}-view B={B} per GPU, bf16, random-init weights",
+                       "backbone": "hrnet-w40" if args.backbone == "hrnet" else "resnet50_paper",
                        "views": views, "image": 256, "batch_per_gpu": B, "micro_batch": args.micro_batch,
                        "parallelism": f"batch-sharded x{world} (replicated weights, NCCL all-gather of poses)",
                        "l2": f"inputs {x.numel() * 4 / 2**20:.0f} MiB + {0.445 * B:.1f} GB of activations per step exceed the 126 MB L2"},
@@ -338,8 +340,9 @@ def run_own(args, lines):
                        "datasets/ho3d.py:35-40 run inside the stem kernel; poses copied back; at most 2 steps in flight); "
                        "sync_call_ms = blocking HandMvNet.forward_host per call"},
             "gpu_launches": launches,
-            "roofline": roofline_report(csv_path, args.steps, step_ms_mean, peaks, views, B, args.micro_batch, tc_ms, tc_flops, tc_n,
-                                        FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9) * value / world * 1e-12, phases),
+            "roofline": roofline_report(csv_path, args.steps, step_ms_mean, peaks, views if args.backbone == "resnet" else 0, B, args.micro_batch, tc_ms, tc_flops, tc_n,
+                                        (FLOP_PER_SAMPLE_HRNET.get(views, 30.42e9 * views + 1.2e9) if args.backbone == "hrnet"
+                                         else FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9)) * value / world * 1e-12, phases),
         }
         if world == 1 and not args.no_cpu_baseline:
             ps, ms, cores = cpu_oracle_throughput(CPU_SAMPLE_B, 10, 3)
@@ -351,8 +354,8 @@ def run_own(args, lines):
     del model
     if world == 1 and rank == 0:
         if not args.no_eager:
-            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, views, B, step_ms_mean)
-        if not args.no_latency:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, views, B, step_ms_mean, args.backbone)
+        if not args.no_latency and args.backbone == "resnet":
             line["latency_b1"] = latency_b1(dev)
     if rank == 0:
         lines.append(json.dumps(line))
@@ -437,7 +440,7 @@ def load_traffic(views, batch, micro_batch):
         return json.load(f)
 
 
-def gpu_eager_baseline(dev, views, B, own_ms):
+def gpu_eager_baseline(dev, views, B, own_ms, backbone="resnet"):
     """The reference's forward as eager PyTorch on THIS GPU (north star: ">= 20x the reference's eager PyTorch forward on
     1 B200 at B=64"): the oracle's full forward (every stage, constants resident on the device) with the protocol of
     src/eval_fps.py:17,79-94 - cudnn.benchmark on, no_grad, fp32 (cuDNN convolutions use TF32 by default, as in the
@@ -446,8 +449,8 @@ def gpu_eager_baseline(dev, views, B, own_ms):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import handmvnet_oracle as O
     torch.cuda.empty_cache()
-    cfg = O.release_config(views, True)
-    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0, randomize_norm=False).items()}
+    cfg = O.release_config(views, True, backbone)
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0, randomize_norm=backbone == "hrnet").items()}
     x, bbox, intr = O.make_inputs(B, views, seed=1234)
     x, bbox, intr = x.to(dev), bbox.to(dev), intr.to(dev)
     prev = torch.backends.cudnn.benchmark
@@ -530,6 +533,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--views", type=int, default=5, help="camera views per sample (5 = HO3D release config, 8 = DexYCB)")
+    ap.add_argument("--backbone", default="resnet", choices=["resnet", "hrnet"], help="resnet = *_HandMvNet.yaml (north star), hrnet = *_HandMvNet_HR.yaml (HRNet-w40)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large-batch sweeps)")
     ap.add_argument("--no-clocks", action="store_true", help="do not run the NVML clock sampler")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg (N=1 only)")
