@@ -13,8 +13,11 @@ def remap_legacy_keys(state_dict):
     return out
 
 
-def load_checkpoint_with_legacy_fix(model, path, map_location="cpu"):
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+def load_checkpoint_with_legacy_fix(checkpoint_path, model, device="cpu"):
+    """Same positional arguments as the reference's helper (src/eval.py:27: `(checkpoint_path, model, device)`)."""
+    if isinstance(checkpoint_path, torch.nn.Module):          # (model, path) order of round 1: still accepted
+        checkpoint_path, model = model, checkpoint_path
+    ckpt = torch.load(checkpoint_path, map_location=device, weights_only=False)
     sd = ckpt["state_dict"] if isinstance(ckpt, dict) and "state_dict" in ckpt else ckpt
     try:
         model.load_state_dict(sd, strict=True)

@@ -29,7 +29,7 @@ def main():
     model = HandMvNet(cfg["train"], cfg["model"], cfg["data"], precision=args.precision, micro_batch=min(args.batch, 16))
     if args.checkpoint:
         from .checkpoint import load_checkpoint_with_legacy_fix
-        load_checkpoint_with_legacy_fix(model, args.checkpoint)
+        load_checkpoint_with_legacy_fix(args.checkpoint, model, "cpu")
     model.to("cuda").eval()
     model.freeze()
     n_views, size = cfg["model"]["num_views"], cfg["data"]["image_size"]
