@@ -108,3 +108,22 @@ def test_create_without_gpu_reports_error():
     assert len(lib.hmv_last_error()) > 0
     with pytest.raises(RuntimeError):
         _lib.check(1, "hmv_create")
+
+
+def test_checkpoint_loader_mirrors_the_reference_helper(tmp_path):
+    """src/eval.py:27-52: `load_checkpoint_with_legacy_fix(checkpoint_path, model, device)` loads a Lightning checkpoint
+    strictly and falls back to the legacy key remap (`pose_net.conv.` -> `pose_net.`, `sample_net.` -> `sample_nets.0.`)."""
+    from handmvnet_b200.checkpoint import load_checkpoint_with_legacy_fix
+    m, _ = _model()
+    sd = O.make_state_dict(O.release_config(5, True), seed=7)
+    legacy = {}
+    for k, v in sd.items():
+        k = k.replace("pose_net.", "pose_net.conv.") if k.startswith("pose_net.") else k
+        k = "sample_net." + k[len("sample_nets.0."):] if k.startswith("sample_nets.0.") else k
+        legacy[k] = v
+    for name, blob in (("new.ckpt", {"state_dict": dict(sd)}), ("legacy.ckpt", {"state_dict": legacy})):
+        path = tmp_path / name
+        torch.save(blob, path)
+        load_checkpoint_with_legacy_fix(str(path), m, "cpu")
+        assert torch.equal(m.state_dict()["pose_net.0.weight"], sd["pose_net.0.weight"])
+        assert torch.equal(m.state_dict()["sample_nets.0.conv.0.weight"], sd["sample_nets.0.conv.0.weight"])
