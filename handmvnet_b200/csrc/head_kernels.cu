@@ -919,24 +919,30 @@ __global__ void __launch_bounds__(128) hr_stem_kernel(const void* __restrict__ x
         float acc[64];
 #pragma unroll
         for (int co = 0; co < 64; ++co) acc[co] = 0.f;
+        // (a fully unrolled tap loop makes ptxas hoist all 432 weight loads: 6 KB of spills per thread; one tap at a time)
+#pragma unroll 1
+        for (int t = 0; t < 27; ++t) {
+            const int r = t / 9, s2 = (t / 3) % 3, c = t % 3;
+            const float a = sx[(c * 3 + r) * pitch + 2 * ox + s2];
+            const float4* wt = reinterpret_cast<const float4*>(sw + t * 64);      // weight layout [cout][r][s][cin] -> tap index (r*3+s)*3+c = t
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 16; ++q) {
+                const float4 wv = wt[q];
+                acc[4 * q] = fmaf(a, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, wv.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(a, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, wv.w, acc[4 * q + 3]);
+            }
+        }
+        // 16-byte stores (64 scalar 2-byte stores per thread made this kernel 30 % of the HRNet step)
+        constexpr int VEC = 16 / sizeof(T);
+        uint4* o = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * wout + oy) * wout + ox) * 64);
 #pragma unroll
-            for (int s2 = 0; s2 < 3; ++s2)
+        for (int v = 0; v < 64 / VEC; ++v) {
+            uint4 q;
+            T* e = reinterpret_cast<T*>(&q);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float a = sx[(c * 3 + r) * pitch + 2 * ox + s2];
-                    const float4* wt = reinterpret_cast<const float4*>(sw + ((r * 3 + s2) * 3 + c) * 64);   // weight layout [cout][r][s][cin] -> tap index (r*3+s)*3+c
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float4 wv = wt[q];
-                        acc[4 * q] = fmaf(a, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(a, wv.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(a, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a, wv.w, acc[4 * q + 3]);
-                    }
-                }
-        T* o = out + ((static_cast<size_t>(n) * wout + oy) * wout + ox) * 64;
-#pragma unroll
-        for (int co = 0; co < 64; ++co) o[co] = from_f<T>(fmaxf(acc[co] + sb[co], 0.f));
+            for (int i = 0; i < VEC; ++i) e[i] = from_f<T>(fmaxf(acc[v * VEC + i] + sb[v * VEC + i], 0.f));
+            o[v] = q;
+        }
     }
 }
 

@@ -79,6 +79,7 @@ struct Layer {
     std::string name;
     int kind = LK_FLAT;
     int cin = 0, cout = 0, ksize = 1, stride = 1, pad = 0;
+    int cin_real = 0;                             // input channels of the layer itself (cin is the buffer's, possibly zero-padded, width)
     int hin = 1, win = 1, hout = 1, wout = 1;     // per image (1x1 for linears)
     int K = 0;                                    // GEMM K in the active precision
     int n_alloc = 0, bn = 0;
@@ -617,7 +618,7 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
     const std::vector<float>& wf = cin_pad != cin ? wpad : wf_in;
     Layer L;
     L.name = name;
-    L.cin = cin_pad; L.cout = cout; L.ksize = k; L.stride = stride; L.pad = k / 2;
+    L.cin = cin_pad; L.cin_real = cin; L.cout = cout; L.ksize = k; L.stride = stride; L.pad = k / 2;
     L.hin = hin; L.win = win; L.hout = hin / stride; L.wout = win / stride;
     L.max_units = h->mb_img;
     L.in = in;
@@ -2248,13 +2249,14 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         cudaEventElapsedTime(&t, r.e0, r.e1);
         const hmv::Layer& L = h->layers[r.layer];
         const double M = static_cast<double>(r.units) * L.rows_per_unit();
-        const double kreal = L.kind == hmv::LK_STEM ? 147.0 : (L.kind == hmv::LK_FLAT ? static_cast<double>(L.cin) : static_cast<double>(L.cin) * L.ksize * L.ksize);
+        const int cin_alg = L.cin_real > 0 ? L.cin_real : L.cin;       // algorithmic work: the layer's own channels, not the padded buffer's
+        const double kreal = L.kind == hmv::LK_STEM ? 147.0 : (L.kind == hmv::LK_FLAT ? static_cast<double>(cin_alg) : static_cast<double>(cin_alg) * L.ksize * L.ksize);
         double flop = 2.0 * M * L.cout * kreal;
         // algorithmic HBM bytes of the launch: every input / residual / output element and every weight once
         auto out_bytes = [&](const hmv::Layer& X, double rows) { return rows * X.cout * (X.ep.out_mode == hmv::OUT_BF16_ROWMAJOR ? 2.0 : 4.0); };
         auto res_bytes = [&](const hmv::Layer& X, double rows) { return X.ep.res_mode == hmv::RES_NONE ? 0.0 : rows * X.cout * (X.ep.res_mode == hmv::RES_BF16 ? 2.0 : 4.0); };
         const double in_rows = L.kind == hmv::LK_FLAT || L.ksize == 1 ? M : static_cast<double>(r.units) * L.hin * L.win;
-        double bytes = in_rows * L.cin * 2.0 + static_cast<double>(L.cout) * L.K * 2.0;
+        double bytes = in_rows * cin_alg * 2.0 + static_cast<double>(L.cout) * kreal * 2.0;
         std::string name = L.name;
         int ncol = L.cout;
         double kcol = kreal;
