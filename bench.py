@@ -342,7 +342,8 @@ def run_own(args, lines):
             "gpu_launches": launches,
             "roofline": roofline_report(csv_path, args.steps, step_ms_mean, peaks, views if args.backbone == "resnet" else 0, B, args.micro_batch, tc_ms, tc_flops, tc_n,
                                         (FLOP_PER_SAMPLE_HRNET.get(views, 30.42e9 * views + 1.2e9) if args.backbone == "hrnet"
-                                         else FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9)) * value / world * 1e-12, phases),
+                                         else FLOP_PER_SAMPLE.get(views, 21.40e9 * views + 1.5e9)) * value / world * 1e-12, phases,
+                                        sm_mhz=(clocks or {}).get("sm_mhz")),
         }
         if world == 1 and not args.no_cpu_baseline:
             ps, ms, cores = cpu_oracle_throughput(CPU_SAMPLE_B, 10, 3)
@@ -371,7 +372,7 @@ def kernel_class(name):
     return name
 
 
-def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, tc_ms, tc_flops, tc_n, model_tflops, phases):
+def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, tc_ms, tc_flops, tc_n, model_tflops, phases, sm_mhz=None, num_sms=148):
     """Per kernel class (launches of one class share a geometry): CUDA-event time per launch, algorithmic FLOPs and HBM
     bytes (SURVEY.md §8d / DESIGN.md §4: every input, residual, output element and every weight once), the roofline
     that bounds the class (the larger of FLOPs / sustained tensor peak and bytes / measured HBM peak) and the achieved
@@ -380,11 +381,12 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
     classes = {}
     with open(csv_path) as f:
         for row in csv.DictReader(f):
-            c = classes.setdefault(kernel_class(row["layer"]), {"n": 0, "ms": 0.0, "gflop": 0.0, "mbytes": 0.0})
+            c = classes.setdefault(kernel_class(row["layer"]), {"n": 0, "ms": 0.0, "gflop": 0.0, "mbytes": 0.0, "mmas": 0.0})
             c["n"] += 1
             c["ms"] += float(row["ms"])
             c["gflop"] += float(row["gflop"])
             c["mbytes"] += float(row["mbytes"])
+            c["mmas"] += float(row.get("mmas") or 0.0)
     tpeak, hpeak = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
     traffic = load_traffic(views, batch, micro_batch)
     out = []
@@ -399,6 +401,14 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
                "peak": tpeak if bound == "tensor" else hpeak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                "frac": max(t_tensor, t_hbm) / ms_l, "tflops": c["gflop"] / c["ms"], "gbs": c["mbytes"] / c["ms"],
                "algorithmic_mbytes_per_launch": c["mbytes"] / c["n"], "gflop_per_launch": c["gflop"] / c["n"]}
+        if c["mmas"] > 0:
+            # tensor-ISSUE floor: an M=128 tcgen05.mma from shared memory costs ~128 cycles whatever N <= 256 is, so a layer
+            # with N = 64 / 128 cannot reach the FLOP roofline; this is what bounds the fused layer1 / layer2 / seam kernels
+            import math
+            mhz = sm_mhz or 1550.0
+            rec["mma_per_launch"] = c["mmas"] / c["n"]
+            rec["issue_floor_ms"] = math.ceil(rec["mma_per_launch"] / num_sms) * 128.0 / (mhz * 1e3)
+            rec["frac_issue"] = rec["issue_floor_ms"] / ms_l
         out.append(rec)
     out.sort(key=lambda r: -r["ms_per_step"])
     top = dict(out[0]) if out else {}
@@ -426,7 +436,9 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
                      "end_to_end_model_tflops": model_tflops}
     top["phase_ms_per_step"] = phases
     top["classes"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
-                       if k in ("kernel", "launches_per_step", "ms_per_launch", "ms_per_step", "bound", "frac", "tflops", "gbs")} for r in out]
+                       if k in ("kernel", "launches_per_step", "ms_per_launch", "ms_per_step", "bound", "frac", "tflops", "gbs", "issue_floor_ms", "frac_issue")} for r in out]
+    top["issue_floor_note"] = ("issue_floor_ms = ceil(tcgen05.mma count / SMs) x 128 cycles at the SM clock sampled during the timed region: the "
+                               "shape-limited tensor floor of a launch (an M=128 MMA costs the same for N = 64, 128 or 256)")
     return top
 
 

@@ -3,7 +3,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhandmvnet_b200.so")
+LIB_PATH = os.environ.get("HMV_LIB_PATH") or os.path.join(HERE, "lib", "libhandmvnet_b200.so")   # HMV_LIB_PATH: A/B builds (tools/)
 
 PRECISION = {"bf16": 0, "fp32": 1}
 STAGE = {"backbone": 0, "pose": 1, "sample": 2, "fusion": 3, "gcn": 4, "softargmax": 5}

@@ -34,10 +34,21 @@ constexpr int kBnNch = kBnN3 / kBnChunk;                        // 8 chunks per 
 constexpr int kBnKb3 = kBnP / kTcBlockK;                        // 4 K blocks per T3
 constexpr int kBnSlotCols = 64;
 constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
-constexpr int kBnSlots = 4;
+// (ring depth is the first-order knob: 5 stages + 4 slots 0.40 ms, 4 + 6 0.49, 3 + 8 0.55 per B=64 launch, with either lag;
+//  the macros exist for that sweep, tools/gpu_r02_variants.sh)
+#ifndef HMV_BN_SLOTS
+#define HMV_BN_SLOTS 4
+#endif
+#ifndef HMV_BN_STAGES
+#define HMV_BN_STAGES 5
+#endif
+#ifndef HMV_BN_LAG
+#define HMV_BN_LAG 1
+#endif
+constexpr int kBnSlots = HMV_BN_SLOTS;
 constexpr int kBnStageBytes = 32 * 1024;                        // T3: A 16 KiB + W3 chunk 16 KiB; T1: W1 K block 32 KiB
-constexpr int kBnStages = 5;
-constexpr int kBnLag = 1;                                        // T1(c - kBnLag) follows T3(c): the epilogue of chunk c-2 is long done by then
+constexpr int kBnStages = HMV_BN_STAGES;
+constexpr int kBnLag = HMV_BN_LAG;                                        // T1(c - kBnLag) follows T3(c): the epilogue of chunk c-2 is long done by then
 constexpr int kBnSlotsPerTile = 2 * kBnNch + kBnP / kBnSlotCols; // 16 conv3 slots + 4 conv1 slots
 constexpr int kBnSmemBytes = kBnStages * kBnStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
 static_assert(kBnSmemBytes <= 227 * 1024, "shared memory budget");

@@ -2243,7 +2243,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
     HMV_CUDA(cudaDeviceSynchronize());
     double ms = 0.0, fl = 0.0;
     FILE* f = csv_path ? fopen(csv_path, "w") : nullptr;
-    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops,mbytes\n");
+    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops,mbytes,mmas\n");
     for (auto& r : h->prof) {
         float t = 0.f;
         cudaEventElapsedTime(&t, r.e0, r.e1);
@@ -2260,13 +2260,19 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         std::string name = L.name;
         int ncol = L.cout;
         double kcol = kreal;
-        if (r.seam >= 0) {                            // fused conv3(b) + conv1(b+1): conv2 output in, residual in, block output + next conv1 output out
+        // tcgen05.mma instructions (M = 128, K = 16) the launch issues: an MMA costs about the same whatever N <= 256 is
+        // (A-operand fetch), so this count x ~128 cycles / SMs is the launch's tensor-issue floor
+        const double m_tiles = L.kind == hmv::LK_FLAT ? ceil(M / 128.0) : static_cast<double>(r.units) * L.tc.p.tpi;
+        double mmas = m_tiles * (L.n_alloc / (L.bn > 0 ? L.bn : 1)) * (L.K / 16.0);
+        if (r.seam >= 0) {
+            mmas = m_tiles * (8.0 * 16.0 + 64.0);     // 8 conv3 chunks x K 256 + next conv1 K 1024                            // fused conv3(b) + conv1(b+1): conv2 output in, residual in, block output + next conv1 output out
             const hmv::Layer& L1 = h->layers[h->seams[r.seam].l1];
             flop += 2.0 * M * L1.cout * L1.cin;
             bytes += out_bytes(L, M) + res_bytes(L, M) + out_bytes(L1, M) + static_cast<double>(L1.cout) * L1.K * 2.0;
             name = L.name + "+next.conv1";
         } else if (r.tail >= 0) {                     // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3 (the conv2 output stays on chip / in L2)
             const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
+            mmas = m_tiles * (L.K / 16.0 + (L3.cout / 128.0) * (L3.K / 16.0));
             flop += 2.0 * M * L3.cout * L3.cin;
             bytes += out_bytes(L3, M) + res_bytes(L3, M) + static_cast<double>(L3.cout) * L3.K * 2.0;
             name = L.name + "+conv3";
@@ -2275,7 +2281,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
             bytes += out_bytes(L, M) + res_bytes(L, M);
         }
         ms += t; fl += flop;
-        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f,%.3f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12, bytes * 1e-6);
+        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f,%.3f,%.0f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12, bytes * 1e-6, mmas);
         h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
     }
     if (f) fclose(f);
