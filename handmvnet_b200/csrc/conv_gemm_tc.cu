@@ -73,10 +73,10 @@ __device__ __forceinline__ void epilogue_16(const Epilogue& ep, const BiasBank& 
 constexpr int kChunkCols = 64;                         // staged output chunk: 128 rows x 64 bf16 = 16 KiB
 constexpr int kChunkBytes = kTcBlockM * kChunkCols * 2;
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool PAIRED = false>
 struct TcCfg {
     static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;       // 16 KiB
-    static constexpr int kBBytes = BN * kTcBlockK * 2;
+    static constexpr int kBBytes = (PAIRED ? BN / 2 : BN) * kTcBlockK * 2;       // a CTA of a cta_group::2 pair holds half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     // staging rings of the TMA-store epilogues (see TcMode)
     static constexpr int kNumS = MODE == TC_DIRECT ? 0 : (MODE == TC_STORE_DEEP ? 4 : 2);     // store slots
@@ -93,6 +93,12 @@ struct TcCfg {
     static_assert(kSmemBytes <= 227 * 1024 && kStages >= 2, "shared memory budget");
 };
 
+// CL = 4: CTA PAIR (tcgen05 cta_group::2).  The two CTAs of a cluster again own two neighbouring M tiles of one N tile, but
+// the leader (rank 0) issues ONE tcgen05.mma of M = 256 per K step for both: each CTA's shared memory holds its own 128 A rows
+// and only HALF of the B tile (its BN/2 rows), each CTA's TMEM receives its own 128 accumulator rows.  Both CTAs' TMA loads
+// count their bytes on the leader's `full` barrier; the leader's tcgen05.commit arrives on `empty` / `tfull` in both CTAs; the
+// peer's epilogue warps arrive on the leader's `tempty` remotely.  Per CTA a stage is 16 + BN/4 KiB instead of 16 + BN/2:
+// for BN = 256 six operand stages fit where four did, and the B operand crosses L2 -> SM once per pair.
 // CL = 2: launched as clusters of two CTAs that work on two neighbouring M tiles of the same N tile at the same time.
 // Each CTA loads its own A tile and ONE HALF of the shared weight tile, multicast into both CTAs' shared memory
 // (tmB then has a BN/2-row box), which halves the L2 -> SM traffic of the B operand.  A stage may only be refilled when
@@ -102,9 +108,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ TcParams p, const __grid_constant__ BiasBank bank) {
-    using Cfg = TcCfg<BN, MODE>;
-    static_assert(CL == 1 || (CL == 2 && BN % 16 == 0), "cluster width");
-    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+    constexpr bool PAIR = CL == 4;
+    using Cfg = TcCfg<BN, MODE, PAIR>;
+    static_assert(CL == 1 || ((CL == 2 || CL == 4) && BN % 32 == 0), "cluster width");
+    const uint32_t crank = CL >= 2 ? cluster_ctarank() : 0u;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kCBytes);
@@ -130,11 +137,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) prefetch_tmap(&tmR);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, CL);                              // one commit per CTA of the cluster
+            mbar_init(empty0 + 8 * i, CL == 2 ? 2 : 1);                 // CL = 2: one commit per CTA of the cluster; pair: the leader's commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, MODE == TC_DIRECT ? 4 : 8);     // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * i, (MODE == TC_DIRECT ? 4 : 8) * (PAIR ? 2 : 1));     // one arrival per epilogue warp (pair: of both CTAs, on the leader)
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(cfull0 + 8 * i, 1);
@@ -143,14 +150,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(static_cast<uint32_t>(Cfg::kTmemCols))
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything remote can land on them
+    if (CL >= 2) cluster_sync_all();   // the peer's barriers are initialised before anything remote can land on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();                        // everything above overlapped the previous kernel; its results are visible from here
@@ -159,10 +173,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Work items.  CL == 1: tile = (m_tile, n_tile), strided by the grid.  CL == 2: the cluster walks (pair of M tiles,
     // n_tile) items and this CTA takes M tile 2 * pair + rank; an M tile past the end is a dummy (zero-filled loads,
     // clipped stores) that still takes part in the stage hand-shake.
-    const int num_tiles = CL == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
-    const int tile0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int tile_step = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    auto m_of = [&](int tile) { return CL == 2 ? 2 * (tile / p.num_n_tiles) + static_cast<int>(crank) : tile / p.num_n_tiles; };
+    const int num_tiles = CL >= 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
+    const int tile0 = CL >= 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = CL >= 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto m_of = [&](int tile) { return CL >= 2 ? 2 * (tile / p.num_n_tiles) + static_cast<int>(crank) : tile / p.num_n_tiles; };
     const int num_kb = p.num_taps * p.cblks;
 
     if (warp == 0) {
@@ -184,6 +198,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 1)) { alive = false; break; }
                         const uint32_t fb = full0 + 8 * stage;
                         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                        if (PAIR) {        // both CTAs' bytes are counted on the LEADER's barrier, which only the leader arms
+                            const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                            if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes));
+                            tma_load_5d_2sm(sa, &tmA, lfb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
+                            tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, lfb, kb * kTcBlockK, n_tile * BN + static_cast<int>(crank) * (BN / 2));
+                            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(fb, static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes);
                         tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
                         if (CL == 2)       // this CTA's half of the weight tile, delivered to both CTAs
@@ -199,15 +221,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
+        if (lane == 0 && !(PAIR && crank != 0)) {          // pair: only the leader issues (for both CTAs)
+            constexpr uint32_t idesc = PAIR ? make_idesc_mn(2 * kTcBlockM, BN) : make_idesc(BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             bool alive = true;
             for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
-                if (!mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, p.err_flag, 2)) { alive = false; break; }
+                if (PAIR ? !mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1, p.err_flag, 2)
+                         : !mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, p.err_flag, 2)) { alive = false; break; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -219,14 +242,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
                         const uint64_t adesc = make_sw128_desc(sa + k * kTcUmmaK * 2);
                         const uint64_t bdesc = make_sw128_desc(sb + k * kTcUmmaK * 2);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (PAIR) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));   // both CTAs' producers wait for both consumers
+                    if (PAIR) umma_commit_2sm_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));  // frees the stage in both CTAs
+                    else if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));   // both CTAs' producers wait for both consumers
                     else umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (!alive) break;
-                umma_commit(tfull0 + 8 * acc);           // accumulator ready for the epilogue
+                if (PAIR) umma_commit_2sm_mc(tfull0 + 8 * acc, static_cast<uint16_t>(3));       // both CTAs' epilogues
+                else umma_commit(tfull0 + 8 * acc);      // accumulator ready for the epilogue
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -282,7 +308,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) {
+                if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));
+                else mbar_arrive(tempty0 + 8 * acc);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -332,7 +361,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (c == BN / kChunkCols - 1) {                // accumulator drained: hand TMEM back early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    if (lane == 0) {
+                        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));
+                        else mbar_arrive(tempty0 + 8 * acc);
+                    }
                 }
                 uint8_t* srow = smem + slab_off + sslot * kChunkBytes;
 #pragma unroll
@@ -377,12 +409,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
+    if (CL >= 2) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(static_cast<uint32_t>(Cfg::kTmemCols))
-                     : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                         : "memory");
     }
 }
 
@@ -398,9 +435,12 @@ template <int BN, int MODE>
 static int set_attr() {
     HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcCfg<BN, MODE>::kSmemBytes));
-    if (BN == 256)
+    if (BN == 256) {
         HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE, BN == 256 ? 2 : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<BN, MODE>::kSmemBytes));
+        HMV_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE, BN == 256 ? 4 : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<BN, MODE, BN == 256>::kSmemBytes));
+    }
     return 0;
 }
 
@@ -477,6 +517,29 @@ int tc_pick_bn(int n) {
 template <int BN, int MODE>
 static int launch_bn(const TcLaunch& l, int num_sms, cudaStream_t stream) {
     if constexpr (BN == 256) {
+        if (l.cluster == 4) {          // CTA pairs issuing cta_group::2 MMAs (l.tmB has a BN/2-row box)
+            static std::map<std::pair<int, int>, int> cache4;
+            int dev = 0;
+            HMV_CUDA(cudaGetDevice(&dev));
+            int& max_clusters = cache4.emplace(std::make_pair(dev, num_sms), -1).first->second;
+            if (max_clusters < 0) {
+                cudaLaunchConfig_t qc{};
+                qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = TcCfg<BN, MODE, true>::kSmemBytes;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa; qc.numAttrs = 1;
+                int n = 0;
+                HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_kernel<BN, MODE, 4>, &qc));
+                HMV_CHECK(n > 0, "no CTA pair of the conv kernel fits on this device");
+                max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+            }
+            const int items = ((l.p.num_m_tiles + 1) / 2) * l.p.num_n_tiles;
+            const int clusters = items < max_clusters ? items : max_clusters;
+            HMV_CUDA(launch_kernel_cluster(conv_gemm_tc_kernel<BN, MODE, 4>, dim3(2 * clusters), dim3(kTcThreads), 2,
+                                           TcCfg<BN, MODE, true>::kSmemBytes, stream, l.tmA, l.tmB, l.tmC, l.tmR, l.p, l.bank));
+            return 0;
+        }
         if (l.cluster == 2) {          // pairs of CTAs sharing multicast weight tiles (l.tmB has a BN/2-row box)
             // the persistent grid must be co-resident: clusters are placed inside one GPC, so fewer than num_sms / 2 may fit
             static std::map<std::pair<int, int>, int> cache;               // per (device, persistent-grid cap)

@@ -433,7 +433,9 @@ static int build_tc(hmv_handle* h, Layer& L) {
     // wide, K-deep layers run as 2-CTA clusters that share multicast weight tiles (conv_gemm_tc.cu, CL = 2)
     static const int cluster_min_k = [] { const char* e = getenv("HMV_CLUSTER_MINK"); return e ? atoi(e) : 512; }();
     t.cluster = (L.bn == 256 && L.K >= cluster_min_k && h->use_clusters && t.p.tile_rows == kTcBlockM) ? 2 : 1;
-    if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster == 2 ? L.bn / 2 : L.bn)) {
+    static const bool pair_mma = [] { const char* e = getenv("HMV_PAIR"); return e && e[0] == '1'; }();   // cta_group::2 MMAs instead of multicast
+    if (t.cluster == 2 && pair_mma) t.cluster = 4;
+    if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster >= 2 ? L.bn / 2 : L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
         return 1;
     }
