@@ -23,6 +23,9 @@
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <map>
+#include <utility>
+
 namespace hmv {
 
 namespace {
@@ -45,13 +48,23 @@ constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
 #ifndef HMV_BN_LAG
 #define HMV_BN_LAG 1
 #endif
+#ifndef HMV_BN_PAIR_STAGES
+#define HMV_BN_PAIR_STAGES 6
+#endif
 constexpr int kBnSlots = HMV_BN_SLOTS;
-constexpr int kBnStageBytes = 32 * 1024;                        // T3: A 16 KiB + W3 chunk 16 KiB; T1: W1 K block 32 KiB
-constexpr int kBnStages = HMV_BN_STAGES;
+// one CTA per tile: T3 stage = A 16 KiB + W3 chunk 16 KiB, T1 stage = W1 K block 32 KiB.
+// CTA pair (cta_group::2, PAIR): a CTA holds its own A rows and HALF of every weight tile: T3 stage = 16 + 8 KiB, T1 stage = 16 KiB
+template <bool PAIR> struct BnGeo {
+    static constexpr int kStageBytes = PAIR ? 24 * 1024 : 32 * 1024;
+    static constexpr int kStages = PAIR ? HMV_BN_PAIR_STAGES : HMV_BN_STAGES;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+constexpr int kBnStageBytes = BnGeo<false>::kStageBytes;
+constexpr int kBnStages = BnGeo<false>::kStages;
 constexpr int kBnLag = HMV_BN_LAG;                                        // T1(c - kBnLag) follows T3(c): the epilogue of chunk c-2 is long done by then
 constexpr int kBnSlotsPerTile = 2 * kBnNch + kBnP / kBnSlotCols; // 16 conv3 slots + 4 conv1 slots
-constexpr int kBnSmemBytes = kBnStages * kBnStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
-static_assert(kBnSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kBnSmemBytes = BnGeo<false>::kSmemBytes;
 
 template <typename F3, typename F1>
 __device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
@@ -76,7 +89,12 @@ __device__ __forceinline__ bool bn_wait(uint32_t bar, uint32_t parity, int* err_
 
 // (A 2-CTA cluster variant with multicast weight tiles was measured at -1 % in round 1 - the kernel is not bound by the
 // L2 -> SM fill bandwidth - and has been removed.)
-template <bool PROF>
+// PAIR: launched as clusters of two CTAs on neighbouring M tiles; the leader (rank 0) issues tcgen05.mma.cta_group::2 of
+// M = 256 for both (A rows from both CTAs' shared memory at the same offsets - operand stages and the epilogue's slots alike -
+// and half of each weight tile from each).  Both CTAs' TMA loads count on the leader's `full` barriers, the leader's commits
+// arrive on `empty` / `t3full` / `t1full` / `sfree` in both CTAs, and the peer's epilogue warps arrive on the leader's
+// `t3empty` / `t1empty` / `aready` remotely.  The weights cross L2 -> SM once per pair and 6 operand stages fit where 5 did.
+template <bool PROF, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 output [rows, 256], load box {64, 128}
                        const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}  
@@ -86,6 +104,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                        const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
                        const __grid_constant__ BnParams p,
                        const __grid_constant__ BiasBank bank) {            // conv3 biases [0, 1024), next conv1 biases [1024, 1280)
+    constexpr int kBnStages = BnGeo<PAIR>::kStages;            // (shadow the single-CTA constants)
+    constexpr int kBnStageBytes = BnGeo<PAIR>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* slots = smem + kBnStages * kBnStageBytes;
@@ -105,6 +125,13 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    constexpr uint32_t kCtas = PAIR ? 2u : 1u;
+    // arrive on a barrier the MMA issuer waits on: in a pair that barrier lives in the leader CTA
+    auto arrive_mma = [&](uint32_t bar) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(bar, 0));
+        else mbar_arrive(bar);
+    };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY2); prefetch_tmap(&tmW3); prefetch_tmap(&tmRes); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmY1);
@@ -114,33 +141,43 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(t3full0 + 8 * i, 1);
-            mbar_init(t3empty0 + 8 * i, 8);                 // one arrival per epilogue warp
+            mbar_init(t3empty0 + 8 * i, 8 * kCtas);         // one arrival per epilogue warp (of both CTAs of a pair)
         }
         mbar_init(t1full, 1);
-        mbar_init(t1empty, 8);
+        mbar_init(t1empty, 8 * kCtas);
         for (int i = 0; i < kBnSlots; ++i) {
             mbar_init(sres0 + 8 * i, 1);
-            mbar_init(aready0 + 8 * i, 4);                   // the four slab warps of the team that handles the slot
+            mbar_init(aready0 + 8 * i, 4 * kCtas);           // the four slab warps of the team that handles the slot (in both CTAs of a pair)
             mbar_init(sfree0 + 8 * i, 5);                   // 4 slab-store issuers + the MMA commit (conv3 slots) / the slot producer (conv1 slots)
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything remote lands on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
     pdl_launch_dependents();
 
-    // this CTA's tiles are blockIdx.x, + gridDim.x, ...
-    const int first = static_cast<int>(blockIdx.x), step = static_cast<int>(gridDim.x);
-    const int n_i = (p.num_m_tiles - first + step - 1) / step;
-    auto tile_of = [&](int i) { return first + i * step; };
+    // one CTA per tile: this CTA's tiles are blockIdx.x, + gridDim.x, ...   pair: the cluster walks pairs of M tiles (the tile
+    // count is even: 8 tiles per image) and this CTA takes tile 2 * pair + rank
+    const int units = PAIR ? p.num_m_tiles / 2 : p.num_m_tiles;
+    const int first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int n_i = (units - first + step - 1) / step;
+    auto tile_of = [&](int i) { return PAIR ? 2 * (first + i * step) + static_cast<int>(crank) : first + i * step; };
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring (same order as the MMA issuer consumes it) =====================
@@ -156,9 +193,16 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51, w_e3)) return false;
                             const uint32_t fb = full0 + 8 * stage;
                             const uint32_t sa = smem_base + stage * kBnStageBytes;
-                            mbar_arrive_expect_tx(fb, kBnStageBytes);
-                            tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
-                            tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            if (PAIR) {            // own A rows + this CTA's 64 of the chunk's 128 weight rows; bytes counted on the leader
+                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (16384u + 8192u));
+                                tma_load_2d_2sm(sa, &tmY2, lfb, kb * kTcBlockK, m * kTcBlockM);
+                                tma_load_2d_2sm(sa + 16384, &tmW3, lfb, kb * kTcBlockK, c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2));
+                            } else {
+                                mbar_arrive_expect_tx(fb, kBnStageBytes);
+                                tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
+                                tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            }
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -167,8 +211,14 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         for (int j = 0; j < 2; ++j) {
                             if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52, w_e1)) return false;
                             const uint32_t fb = full0 + 8 * stage;
-                            mbar_arrive_expect_tx(fb, kBnStageBytes);
-                            tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            if (PAIR) {            // this CTA's 128 of the 256 weight rows of the K block
+                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * 16384u);
+                                tma_load_2d_2sm(smem_base + stage * kBnStageBytes, &tmW1, lfb, (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2));
+                            } else {
+                                mbar_arrive_expect_tx(fb, kBnStageBytes);
+                                tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            }
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -180,9 +230,24 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc3 = make_idesc(kBnChunk);
-            constexpr uint32_t idesc1 = make_idesc(kBnP);
+        if (lane == 0 && crank == 0) {                       // pair: only the leader issues, for both CTAs
+            constexpr uint32_t idesc3 = PAIR ? make_idesc_mn(2 * kTcBlockM, kBnChunk) : make_idesc(kBnChunk);
+            constexpr uint32_t idesc1 = PAIR ? make_idesc_mn(2 * kTcBlockM, kBnP) : make_idesc(kBnP);
+            auto wait_epi = [&](uint32_t bar, uint32_t parity, int code, long long& acc) {      // barriers the epilogue warps arrive on
+                if (!PAIR) return bn_wait<PROF>(bar, parity, p.err_flag, code, acc);
+                const long long t0 = PROF ? clock64() : 0;
+                const bool ok = mbar_wait_cluster(bar, parity, p.err_flag, code);
+                if (PROF) acc += clock64() - t0;
+                return ok;
+            };
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+                if (PAIR) umma_f16_2sm(d, a, b, idesc, accum);
+                else umma_f16(d, a, b, idesc, accum);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) umma_commit_2sm_mc(bar, static_cast<uint16_t>(3));
+                else umma_commit(bar);
+            };
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q3 = 0;                                 // running conv3 chunk counter (TMEM slot = q3 & 1)
@@ -193,22 +258,22 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                 const bool ok = bn_tile_schedule(
                     [&](int) {
                         const uint32_t s = q3 & 1u, use = q3 >> 1;
-                        if (!bn_wait<PROF>(t3empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 53, w_t3e)) return false;
+                        if (!wait_epi(t3empty0 + 8 * s, (use & 1u) ^ 1u, 53, w_t3e)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBnP + s * kBnChunk;
                         for (int kb = 0; kb < kBnKb3; ++kb) {
                             if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 54, w_f3)) return false;
                             tc_fence_after();
                             const uint32_t sa = smem_base + stage * kBnStageBytes;
-                            const uint32_t sb = sa + kBnStageBytes / 2;
+                            const uint32_t sb = sa + 16384;
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
-                                         (kb | k) != 0 ? 1u : 0u);
-                            umma_commit(empty0 + 8 * stage);
+                                mma(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
+                                    (kb | k) != 0 ? 1u : 0u);
+                            commit(empty0 + 8 * stage);
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit(t3full0 + 8 * s);
+                        commit(t3full0 + 8 * s);
                         ++q3;
                         return true;
                     },
@@ -216,22 +281,22 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t g = gbase + 2 * c + j, slot = g % kBnSlots, use = g / kBnSlots;
                             if (c == 0 && j == 0) {          // acc1 drained by the epilogue of the previous tile
-                                if (!bn_wait<PROF>(t1empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, p.err_flag, 55, w_t1e)) return false;
+                                if (!wait_epi(t1empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, 55, w_t1e)) return false;
                             }
-                            if (!bn_wait<PROF>(aready0 + 8 * slot, use & 1u, p.err_flag, 56, w_ar)) return false;
+                            if (!wait_epi(aready0 + 8 * slot, use & 1u, 56, w_ar)) return false;
                             if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 57, w_f1)) return false;
                             tc_fence_after();
                             const uint32_t sa = slots_base + slot * kBnSlotBytes;          // finished block-output chunk = A operand
                             const uint32_t sb = smem_base + stage * kBnStageBytes;
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                umma_f16(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
-                                         (c | j | k) != 0 ? 1u : 0u);
-                            umma_commit(empty0 + 8 * stage);
-                            umma_commit(sfree0 + 8 * slot);                                // the slot's MMAs have retired
+                                mma(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
+                                    (c | j | k) != 0 ? 1u : 0u);
+                            commit(empty0 + 8 * stage);
+                            commit(sfree0 + 8 * slot);                                     // the slot's MMAs have retired (in both CTAs of a pair)
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
-                        if (c == kBnNch - 1) umma_commit(t1full);
+                        if (c == kBnNch - 1) commit(t1full);
                         return true;
                     });
                 if (!ok) break;
@@ -311,7 +376,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                 if (hf == 1 && release_bar != 0) {           // this warp's part of the accumulator is read: hand TMEM back early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(release_bar);
+                    if (lane == 0) arrive_mma(release_bar);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -334,7 +399,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             __syncwarp();
             if (PROF) { const long long t0 = clock64(); w_fence += t0 - tp; tp = t0; }
             if (lane == 0) {
-                mbar_arrive(aready0 + 8 * slot);             // every slot use (conv1 slots too: keeps the barrier's phase == use count)
+                arrive_mma(aready0 + 8 * slot);              // every slot use (conv1 slots too: keeps the barrier's phase == use count)
                 tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
                 bulk_commit();
                 pending = static_cast<int>(slot);
@@ -378,29 +443,61 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer may still arrive on this CTA's barriers / the leader's MMAs read this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 }  // namespace
 
 int bn_init() {
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BnGeo<false>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BnGeo<false>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BnGeo<true>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_next_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BnGeo<true>::kSmemBytes));
     return 0;
 }
 
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0) return 0;
+    if (l.pair) {                      // CTA pairs (tmW3 / tmW1 carry half-height boxes)
+        HMV_CHECK(l.p.num_m_tiles % 2 == 0, "seam kernel pairs need an even tile count");
+        static std::map<std::pair<int, int>, int> cache;                   // per (device, persistent-grid cap)
+        int dev = 0;
+        HMV_CUDA(cudaGetDevice(&dev));
+        int& max_clusters = cache.emplace(std::make_pair(dev, num_sms), -1).first->second;
+        if (max_clusters < 0) {        // the persistent grid must be co-resident; clusters are placed inside one GPC
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = BnGeo<true>::kSmemBytes;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int n = 0;
+            HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, bottleneck_next_kernel<false, true>, &qc));
+            HMV_CHECK(n > 0, "no CTA pair of the seam kernel fits on this device");
+            max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+        }
+        const int pairs = l.p.num_m_tiles / 2;
+        const int clusters = pairs < max_clusters ? pairs : max_clusters;
+        if (l.p.prof)
+            HMV_CUDA(launch_kernel_cluster(bottleneck_next_kernel<true, true>, dim3(2 * clusters), dim3(kTcThreads), 2, BnGeo<true>::kSmemBytes, stream,
+                                           l.tmY2, l.tmW3, l.tmRes, l.tmOut, l.tmW1, l.tmY1, l.p, l.bank));
+        else
+            HMV_CUDA(launch_kernel_cluster(bottleneck_next_kernel<false, true>, dim3(2 * clusters), dim3(kTcThreads), 2, BnGeo<true>::kSmemBytes, stream,
+                                           l.tmY2, l.tmW3, l.tmRes, l.tmOut, l.tmW1, l.tmY1, l.p, l.bank));
+        return 0;
+    }
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
     if (l.p.prof)
-        HMV_CUDA(launch_kernel(bottleneck_next_kernel<true>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
-                               l.tmW1, l.tmY1, l.p, l.bank));
+        HMV_CUDA(launch_kernel(bottleneck_next_kernel<true, false>, dim3(grid), dim3(kTcThreads), BnGeo<false>::kSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes,
+                               l.tmOut, l.tmW1, l.tmY1, l.p, l.bank));
     else
-        HMV_CUDA(launch_kernel(bottleneck_next_kernel<false>, dim3(grid), dim3(kTcThreads), kBnSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes, l.tmOut,
-                               l.tmW1, l.tmY1, l.p, l.bank));
+        HMV_CUDA(launch_kernel(bottleneck_next_kernel<false, false>, dim3(grid), dim3(kTcThreads), BnGeo<false>::kSmemBytes, stream, l.tmY2, l.tmW3, l.tmRes,
+                               l.tmOut, l.tmW1, l.tmY1, l.p, l.bank));
     return 0;
 }
 

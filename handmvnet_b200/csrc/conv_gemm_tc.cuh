@@ -100,6 +100,7 @@ struct BnLaunch {
     BiasBank bank;
     CUtensorMap tmY2, tmW3, tmRes, tmOut, tmW1, tmY1;
     BnParams p;
+    int pair;                          // 1: CTA pairs issuing cta_group::2 MMAs (tmW3 / tmW1 are half-height boxes)
 };
 int bn_init();
 int bn_launch(const BnLaunch& l, int num_sms, cudaStream_t stream);

@@ -433,8 +433,13 @@ static int build_tc(hmv_handle* h, Layer& L) {
     // wide, K-deep layers run as 2-CTA clusters that share multicast weight tiles (conv_gemm_tc.cu, CL = 2)
     static const int cluster_min_k = [] { const char* e = getenv("HMV_CLUSTER_MINK"); return e ? atoi(e) : 512; }();
     t.cluster = (L.bn == 256 && L.K >= cluster_min_k && h->use_clusters && t.p.tile_rows == kTcBlockM) ? 2 : 1;
-    static const bool pair_mma = [] { const char* e = getenv("HMV_PAIR"); return e && e[0] == '1'; }();   // cta_group::2 MMAs instead of multicast
-    if (t.cluster == 2 && pair_mma) t.cluster = 4;
+    // cta_group::2 CTA pairs (one M = 256 MMA per K step for two tiles, half of B per CTA, 6 operand stages) instead of the
+    // multicast clusters, for the K-deep layers of large passes: measured at B = 64 l3.conv2 0.279 -> 0.267 ms, pose_net.0
+    // 0.284 -> 0.250; short-K layers (K = 512 / 576: downsample, l3.0.conv1, QKV) get 5-10 % slower because the pair couples
+    // two epilogues to one MMA issuer.  HMV_PAIR=0 disables, HMV_PAIR_MINK=<K> moves the threshold.
+    static const bool pair_mma = [] { const char* e = getenv("HMV_PAIR"); return !(e && e[0] == '0'); }();
+    static const int pair_min_k = [] { const char* e = getenv("HMV_PAIR_MINK"); return e ? atoi(e) : 1024; }();
+    if (t.cluster == 2 && pair_mma && L.K >= pair_min_k && static_cast<int64_t>(L.max_units) * L.rows_per_unit() >= 65536) t.cluster = 4;
     if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster >= 2 ? L.bn / 2 : L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
         return 1;
@@ -753,8 +758,12 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
     BnLaunch& b = S.bn;
     memset(&b.p, 0, sizeof(b.p));
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
-    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, 128) ||
-        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, 256)) {
+    // CTA-pair variant of the seam kernel (cta_group::2): 0.408 -> 0.396 ms per B = 64 launch; small passes keep one CTA per tile
+    static const bool seam_pair_env = [] { const char* e = getenv("HMV_SEAM_PAIR"); return !(e && e[0] == '0'); }();
+    const bool seam_pair = seam_pair_env && rows >= 65536;
+    b.pair = seam_pair ? 1 : 0;
+    if (tc_make_tmap_out(&b.tmY2, A.in, 256, rows, 128) || tc_make_tmap_out(&b.tmW3, A.w, 256, 1024, seam_pair ? 64 : 128) ||
+        tc_make_tmap_wgt(&b.tmW1, B.w, 1024, 256, seam_pair ? 128 : 256)) {
         set_error(std::string(get_error()) + " [fused-seam maps of " + name + "]");
         return 1;
     }

@@ -101,7 +101,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {           // arrive on a barrier of any CTA of the cluster
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release.cta), as in CUTLASS' ClusterBarrier::arrive(cta_id): the .release.cluster form was measured
+    // 3x slower on the epilogue's critical path; what is published here is ordered by tcgen05 / proxy fences issued before
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
     uint32_t ok;
