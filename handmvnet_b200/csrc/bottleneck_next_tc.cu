@@ -181,7 +181,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring (same order as the MMA issuer consumes it) =====================
-        if (lane == 0) {
+        {   // the whole warp walks the schedule and waits; one elected lane issues the copies (see elect_one() in tc_ptx.cuh)
             int stage = 0;
             uint32_t phase = 0;
             long long w_e3 = 0, w_e1 = 0;
@@ -191,18 +191,21 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     [&](int c) {
                         for (int kb = 0; kb < kBnKb3; ++kb) {
                             if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51, w_e3)) return false;
-                            const uint32_t fb = full0 + 8 * stage;
-                            const uint32_t sa = smem_base + stage * kBnStageBytes;
-                            if (PAIR) {            // own A rows + this CTA's 64 of the chunk's 128 weight rows; bytes counted on the leader
-                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
-                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (16384u + 8192u));
-                                tma_load_2d_2sm(sa, &tmY2, lfb, kb * kTcBlockK, m * kTcBlockM);
-                                tma_load_2d_2sm(sa + 16384, &tmW3, lfb, kb * kTcBlockK, c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2));
-                            } else {
-                                mbar_arrive_expect_tx(fb, kBnStageBytes);
-                                tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
-                                tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                            if (elect_one()) {
+                                const uint32_t fb = full0 + 8 * stage;
+                                const uint32_t sa = smem_base + stage * kBnStageBytes;
+                                if (PAIR) {        // own A rows + this CTA's 64 of the chunk's 128 weight rows; bytes counted on the leader
+                                    const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (16384u + 8192u));
+                                    tma_load_2d_2sm(sa, &tmY2, lfb, kb * kTcBlockK, m * kTcBlockM);
+                                    tma_load_2d_2sm(sa + 16384, &tmW3, lfb, kb * kTcBlockK, c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2));
+                                } else {
+                                    mbar_arrive_expect_tx(fb, kBnStageBytes);
+                                    tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
+                                    tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+                                }
                             }
+                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -210,27 +213,31 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     [&](int c) {
                         for (int j = 0; j < 2; ++j) {
                             if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 52, w_e1)) return false;
-                            const uint32_t fb = full0 + 8 * stage;
-                            if (PAIR) {            // this CTA's 128 of the 256 weight rows of the K block
-                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
-                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * 16384u);
-                                tma_load_2d_2sm(smem_base + stage * kBnStageBytes, &tmW1, lfb, (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2));
-                            } else {
-                                mbar_arrive_expect_tx(fb, kBnStageBytes);
-                                tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                            if (elect_one()) {
+                                const uint32_t fb = full0 + 8 * stage;
+                                if (PAIR) {        // this CTA's 128 of the 256 weight rows of the K block
+                                    const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * 16384u);
+                                    tma_load_2d_2sm(smem_base + stage * kBnStageBytes, &tmW1, lfb, (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2));
+                                } else {
+                                    mbar_arrive_expect_tx(fb, kBnStageBytes);
+                                    tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
+                                }
                             }
+                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
                     });
                 if (!ok) break;
             }
-            if (PROF && p.prof) { p.prof[blockIdx.x * 24 + 6] = w_e3; p.prof[blockIdx.x * 24 + 7] = w_e1; }
+            if (PROF && p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 6] = w_e3; p.prof[blockIdx.x * 24 + 7] = w_e1; }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && crank == 0) {                       // pair: only the leader issues, for both CTAs
+        if (crank == 0) {                                    // pair: only the leader issues, for both CTAs
+            // the whole warp walks the schedule and waits; one elected lane issues (see elect_one() in tc_ptx.cuh for why)
             constexpr uint32_t idesc3 = PAIR ? make_idesc_mn(2 * kTcBlockM, kBnChunk) : make_idesc(kBnChunk);
             constexpr uint32_t idesc1 = PAIR ? make_idesc_mn(2 * kTcBlockM, kBnP) : make_idesc(kBnP);
             auto wait_epi = [&](uint32_t bar, uint32_t parity, int code, long long& acc) {      // barriers the epilogue warps arrive on
@@ -264,16 +271,18 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         for (int kb = 0; kb < kBnKb3; ++kb) {
                             if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 54, w_f3)) return false;
                             tc_fence_after();
-                            const uint32_t sa = smem_base + stage * kBnStageBytes;
-                            const uint32_t sb = sa + 16384;
+                            if (elect_one()) {
+                                const uint64_t adesc = make_sw128_desc(smem_base + stage * kBnStageBytes);
+                                const uint64_t bdesc = make_sw128_desc(smem_base + stage * kBnStageBytes + 16384);
 #pragma unroll
-                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                mma(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
-                                    (kb | k) != 0 ? 1u : 0u);
-                            commit(empty0 + 8 * stage);
+                                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
+                                    mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb | k) != 0 ? 1u : 0u);
+                                commit(empty0 + 8 * stage);
+                                if (kb == kBnKb3 - 1) commit(t3full0 + 8 * s);
+                            }
+                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
-                        commit(t3full0 + 8 * s);
                         ++q3;
                         return true;
                     },
@@ -286,22 +295,24 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             if (!wait_epi(aready0 + 8 * slot, use & 1u, 56, w_ar)) return false;
                             if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 57, w_f1)) return false;
                             tc_fence_after();
-                            const uint32_t sa = slots_base + slot * kBnSlotBytes;          // finished block-output chunk = A operand
-                            const uint32_t sb = smem_base + stage * kBnStageBytes;
+                            if (elect_one()) {
+                                const uint64_t adesc = make_sw128_desc(slots_base + slot * kBnSlotBytes);   // finished block-output chunk = A operand
+                                const uint64_t bdesc = make_sw128_desc(smem_base + stage * kBnStageBytes);
 #pragma unroll
-                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                mma(tmem_base, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc1,
-                                    (c | j | k) != 0 ? 1u : 0u);
-                            commit(empty0 + 8 * stage);
-                            commit(sfree0 + 8 * slot);                                     // the slot's MMAs have retired (in both CTAs of a pair)
+                                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                                    mma(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc1, (c | j | k) != 0 ? 1u : 0u);
+                                commit(empty0 + 8 * stage);
+                                commit(sfree0 + 8 * slot);                                 // the slot's MMAs have retired (in both CTAs of a pair)
+                                if (c == kBnNch - 1 && j == 1) commit(t1full);
+                            }
+                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
-                        if (c == kBnNch - 1) commit(t1full);
                         return true;
                     });
                 if (!ok) break;
             }
-            if (PROF && p.prof) {
+            if (PROF && p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 24;
                 o[0] = clock64() - t_start; o[1] = w_t3e; o[2] = w_f3; o[3] = w_t1e; o[4] = w_ar; o[5] = w_f1; o[15] = n_i;
             }
@@ -309,7 +320,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         __syncwarp();
     } else if (warp == 2) {
         // ===================== slot producer: residual prefetch (conv3 slots) / plain hand-over (conv1 slots) =====================
-        if (lane == 0) {
+        {   // whole warp + one elected lane per copy, as above
             uint32_t g = 0;
             bool alive = true;
             long long w_sf = 0;
@@ -318,16 +329,19 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                 for (int c = 0; c < kBnSlotsPerTile && alive; ++c, ++g) {
                     const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
                     if (!bn_wait<PROF>(sfree0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 58, w_sf)) { alive = false; break; }
-                    if (c < 2 * kBnNch) {
-                        mbar_arrive_expect_tx(sres0 + 8 * slot, kBnSlotBytes);
-                        tma_load_2d(slots_base + slot * kBnSlotBytes, &tmRes, sres0 + 8 * slot, c * kBnSlotCols, m * kTcBlockM);
-                    } else {
-                        mbar_arrive(sres0 + 8 * slot);
-                        mbar_arrive(sfree0 + 8 * slot);      // stands in for the MMA commit: conv1 slots feed no MMA
+                    if (elect_one()) {
+                        if (c < 2 * kBnNch) {
+                            mbar_arrive_expect_tx(sres0 + 8 * slot, kBnSlotBytes);
+                            tma_load_2d(slots_base + slot * kBnSlotBytes, &tmRes, sres0 + 8 * slot, c * kBnSlotCols, m * kTcBlockM);
+                        } else {
+                            mbar_arrive(sres0 + 8 * slot);
+                            mbar_arrive(sfree0 + 8 * slot);  // stands in for the MMA commit: conv1 slots feed no MMA
+                        }
                     }
+                    __syncwarp();
                 }
             }
-            if (PROF && p.prof) p.prof[blockIdx.x * 24 + 8] = w_sf;
+            if (PROF && p.prof && lane == 0) p.prof[blockIdx.x * 24 + 8] = w_sf;
         }
         __syncwarp();
     } else if (warp >= 4) {

@@ -72,7 +72,8 @@ __device__ __forceinline__ bool bt_segment(bool has_t2, bool has_t3, F2&& kblock
 }
 
 // mbar_wait that also accumulates the stall time (clock cycles) into `acc` -- read back by HMV_BT_PROF=1 runs
-__device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* err_flag, int code, long long& acc) {
+__device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* err_flag, int code, long long& acc, bool prof) {
+    if (!prof) return mbar_wait(bar, parity, err_flag, code);
     const long long t0 = clock64();                  // (try_wait may suspend inside the instruction: time it as well)
     const bool ok = mbar_wait(bar, parity, err_flag, code);
     acc += clock64() - t0;
@@ -148,10 +149,11 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 
     const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+    const bool prof = p.prof != nullptr;
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring =====================
-        if (lane == 0) {
+        {   // the whole warp walks the schedule and waits; one elected lane issues the copies (see elect_one() in tc_ptx.cuh)
             int stage = 0;
             uint32_t phase = 0;
             long long w_empty = 0, w_y2 = 0;
@@ -161,46 +163,52 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 const int h0 = (m2 % p.tpi) * p.hbox, img = m2 / p.tpi;
                 const bool ok = bt_segment<P>(i < n_i, j3 >= 0,
                     [&](int kb) {
-                        if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 21, w_empty)) return false;
-                        const TcTap tap = p.taps[kb / p.cblks];
-                        const int cb = kb % p.cblks;
-                        const uint32_t fb = full0 + 8 * stage;
-                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                        mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB2Bytes);
-                        tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
-                        tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
+                        if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 21, w_empty, prof)) return false;
+                        if (elect_one()) {
+                            const TcTap tap = p.taps[kb / (P / kTcBlockK)];
+                            const int cb = kb % (P / kTcBlockK);
+                            const uint32_t fb = full0 + 8 * stage;
+                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                            mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB2Bytes);
+                            tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
+                            tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
+                        }
+                        __syncwarp();
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         return true;
                     },
                     [&](int c) {
                         // Y2[m3] was TMA-stored by this CTA's epilogue; wait until those stores have completed
-                        if (c == 0 && !timed_wait(y2ready0 + 8 * (j3 & 1), static_cast<uint32_t>(j3 >> 1) & 1u, p.err_flag, 22, w_y2)) return false;
-                        if (c == 0) fence_proxy_async_all();
+                        if (c == 0 && !timed_wait(y2ready0 + 8 * (j3 & 1), static_cast<uint32_t>(j3 >> 1) & 1u, p.err_flag, 22, w_y2, prof)) return false;
+                        if (c == 0) fence_proxy_async_all();      // (every lane: the elected one is not known in advance)
                         for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
-                            if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 23, w_empty)) return false;
-                            const uint32_t fb = full0 + 8 * stage;
-                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                            mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
-                            tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
-                            tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                            if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 23, w_empty, prof)) return false;
+                            if (elect_one()) {
+                                const uint32_t fb = full0 + 8 * stage;
+                                const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                                mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
+                                tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
+                                tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                            }
+                            __syncwarp();
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
                     });
                 if (!ok) break;
             }
-            if (p.prof) { p.prof[blockIdx.x * 16 + 5] = w_empty; p.prof[blockIdx.x * 16 + 6] = w_y2; }
+            if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 5] = w_empty; p.prof[blockIdx.x * 16 + 6] = w_y2; }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {   // the whole warp walks the schedule and waits; one elected lane issues (see elect_one() in tc_ptx.cuh for why)
             constexpr uint32_t idesc2 = make_idesc(P);
             constexpr uint32_t idesc3 = make_idesc(kBtN3);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q = 0;                                  // running conv3 chunk counter (TMEM slot = q & 1)
-            long long w_t1e = 0, w_f2 = 0, w_t2e = 0, w_f3 = 0;
+            long long w_t1e = 0, w_f2 = 0, w_t2e = 0, w_f3 = 0, t_issue = 0;
             const long long t_start = clock64();
             for (int i = 0; i < n_i + kBtLag; ++i) {
                 const uint32_t a = static_cast<uint32_t>(i) % Cfg::kNA, ause = static_cast<uint32_t>(i) / Cfg::kNA;
@@ -208,78 +216,90 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 const bool ok = bt_segment<P>(i < n_i, i >= kBtLag,
                     [&](int kb) {
                         if (kb == 0) {                       // this conv2 accumulator was drained by the epilogue of its previous tile
-                            if (!timed_wait(t1empty0 + 8 * a, (ause & 1u) ^ 1u, p.err_flag, 24, w_t1e)) return false;
+                            if (!timed_wait(t1empty0 + 8 * a, (ause & 1u) ^ 1u, p.err_flag, 24, w_t1e, prof)) return false;
                             tc_fence_after();
                         }
-                        if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 25, w_f2)) return false;
+                        if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 25, w_f2, prof)) return false;
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                        const uint32_t sb = sa + Cfg::kABytes;
+                        const long long c0 = p.prof ? clock64() : 0;
+                        if (elect_one()) {
+                            const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
+                            const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
 #pragma unroll
-                        for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                            umma_f16(acc1, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc2,
-                                     (kb | k) != 0 ? 1u : 0u);
-                        umma_commit(empty0 + 8 * stage);
+                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
+                                umma_f16(acc1, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                            umma_commit(empty0 + 8 * stage);
+                            if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
+                        }
+                        __syncwarp();
+                        if (p.prof) t_issue += clock64() - c0;
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-                        if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
                         return true;
                     },
                     [&](int) {
                         const uint32_t s = q & 1u, use = q >> 1;
-                        if (!timed_wait(t2empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 26, w_t2e)) return false;
+                        if (!timed_wait(t2empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 26, w_t2e, prof)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBtAcc2Col + s * kBtN3;
                         for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
-                            if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 27, w_f3)) return false;
+                            if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 27, w_f3, prof)) return false;
                             tc_fence_after();
-                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                            const uint32_t sb = sa + Cfg::kABytes;
+                            const long long c0 = p.prof ? clock64() : 0;
+                            if (elect_one()) {
+                                const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
+                                const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
 #pragma unroll
-                            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                umma_f16(d_tmem, make_sw128_desc(sa + k * kTcUmmaK * 2), make_sw128_desc(sb + k * kTcUmmaK * 2), idesc3,
-                                         (kb3 | k) != 0 ? 1u : 0u);
-                            umma_commit(empty0 + 8 * stage);
+                                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
+                                    umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb3 | k) != 0 ? 1u : 0u);
+                                umma_commit(empty0 + 8 * stage);
+                                if (kb3 == Cfg::kKB3 - 1) umma_commit(t2full0 + 8 * s);
+                            }
+                            __syncwarp();
+                            if (p.prof) t_issue += clock64() - c0;
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit(t2full0 + 8 * s);
                         ++q;
                         return true;
                     });
                 if (!ok) break;
             }
-            if (p.prof) {
+            if (p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 16;
-                o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i;
+                o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i; o[14] = t_issue; o[15] = 0;
             }
         }
         __syncwarp();
     } else if (warp == 2) {
         // ===================== chunk-slot producer: residual prefetch (conv3 chunks) / plain hand-over (conv2 chunks) ============
-        if (lane == 0) {
+        {   // whole warp + one elected lane per copy, as above
             uint32_t g = 0;
             bool alive = true;
             long long w_ce = 0;
             for (int i = 0; i < n_i + kBtLag && alive; ++i) {
-                if (p.prefetch && i + 1 >= kBtLag && i + 1 - kBtLag < n_i)      // next segment's residual tile: HBM -> L2 ahead of its slot loads
+                if (p.prefetch && i + 1 >= kBtLag && i + 1 - kBtLag < n_i && lane == 0)      // next segment's residual tile: HBM -> L2 ahead of its slot loads
                     for (int c = 0; c < Cfg::kNCH * 2; ++c) tma_prefetch_l2_2d(&tmRes, c * kBtChunkCols, tile_of(i + 1 - kBtLag) * kTcBlockM);
+                __syncwarp();
                 if (i >= kBtLag) {
                     const int m3 = tile_of(i - kBtLag);
                     for (int c = 0; c < Cfg::kNCH * 2 && alive; ++c, ++g) {
                         const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
-                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 28, w_ce)) { alive = false; break; }
-                        mbar_arrive_expect_tx(cfull0 + 8 * slot, kBtChunkBytes);
-                        tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
+                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 28, w_ce, prof)) { alive = false; break; }
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(cfull0 + 8 * slot, kBtChunkBytes);
+                            tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
+                        }
+                        __syncwarp();
                     }
                 }
                 if (i < n_i) {
                     for (int c = 0; c < P / kBtChunkCols && alive; ++c, ++g) {
                         const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
-                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 29, w_ce)) { alive = false; break; }
-                        mbar_arrive(cfull0 + 8 * slot);
+                        if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 29, w_ce, prof)) { alive = false; break; }
+                        if (lane == 0) mbar_arrive(cfull0 + 8 * slot);
                     }
                 }
             }
-            if (p.prof) p.prof[blockIdx.x * 16 + 12] = w_ce;
+            if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 12] = w_ce;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -307,7 +327,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 float4 bq[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) bq[j] = *reinterpret_cast<const float4*>(&bank.v[bias_off + hf * 32 + 4 * j]);   // constant cache
-                if (hf == 0 && !timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf)) alive = false;
+                if (hf == 0 && !timed_wait(cfull0 + 8 * slot, use & 1u, p.err_flag, 30, w_cf, prof)) alive = false;
                 uint4 rq[4];
                 if (has_res) {
 #pragma unroll
@@ -364,7 +384,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 for (int c = 0; c < Cfg::kNCH && alive; ++c, ++q) {
                     const uint32_t s = q & 1u;
                     release_pending();
-                    if (!timed_wait(t2full0 + 8 * s, (q >> 1) & 1u, p.err_flag, 31, w_t2f)) { alive = false; break; }
+                    if (!timed_wait(t2full0 + 8 * s, (q >> 1) & 1u, p.err_flag, 31, w_t2f, prof)) { alive = false; break; }
                     tc_fence_after();
 #pragma unroll 1
                     for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc, ++g) {     // two chunks: one per team
@@ -382,7 +402,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 for (int cc = 0; cc < kN2; ++cc) mine = mine || (((g + cc) & 1u) == team);
                 if (mine) {
                     release_pending();
-                    if (!timed_wait(t1full0 + 8 * a, ause & 1u, p.err_flag, 32, w_t1f)) { alive = false; break; }
+                    if (!timed_wait(t1full0 + 8 * a, ause & 1u, p.err_flag, 32, w_t1f, prof)) { alive = false; break; }
                     tc_fence_after();
                 }
 #pragma unroll 1

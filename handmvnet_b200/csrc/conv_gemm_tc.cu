@@ -181,7 +181,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer (A / B operand tiles) =====================
-        if (lane == 0) {
+        {   // the whole warp walks the schedule and waits; one elected lane issues the copies (see elect_one() in tc_ptx.cuh)
             int stage = 0;
             uint32_t phase = 0;
             bool alive = true;
@@ -196,23 +196,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const TcTap tap = p.taps[t];
                     for (int cb = 0; cb < p.cblks; ++cb, ++kb) {
                         if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 1)) { alive = false; break; }
-                        const uint32_t fb = full0 + 8 * stage;
-                        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                        if (PAIR) {        // both CTAs' bytes are counted on the LEADER's barrier, which only the leader arms
-                            const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
-                            if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes));
-                            tma_load_5d_2sm(sa, &tmA, lfb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
-                            tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, lfb, kb * kTcBlockK, n_tile * BN + static_cast<int>(crank) * (BN / 2));
-                            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-                            continue;
+                        if (elect_one()) {
+                            const uint32_t fb = full0 + 8 * stage;
+                            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                            if (PAIR) {    // both CTAs' bytes are counted on the LEADER's barrier, which only the leader arms
+                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes));
+                                tma_load_5d_2sm(sa, &tmA, lfb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
+                                tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, lfb, kb * kTcBlockK, n_tile * BN + static_cast<int>(crank) * (BN / 2));
+                            } else {
+                                mbar_arrive_expect_tx(fb, static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes);
+                                tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
+                                if (CL == 2)   // this CTA's half of the weight tile, delivered to both CTAs
+                                    tma_load_2d_mc(sa + Cfg::kABytes + crank * (Cfg::kBBytes / 2), &tmB, fb, kb * kTcBlockK,
+                                                   n_tile * BN + static_cast<int>(crank) * (BN / 2), static_cast<uint16_t>(3));
+                                else
+                                    tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
+                            }
                         }
-                        mbar_arrive_expect_tx(fb, static_cast<uint32_t>(p.a_bytes) + Cfg::kBBytes);
-                        tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, w0 + tap.dw, tap.a, h0 + tap.dh, img);
-                        if (CL == 2)       // this CTA's half of the weight tile, delivered to both CTAs
-                            tma_load_2d_mc(sa + Cfg::kABytes + crank * (Cfg::kBBytes / 2), &tmB, fb, kb * kTcBlockK,
-                                           n_tile * BN + static_cast<int>(crank) * (BN / 2), static_cast<uint16_t>(3));
-                        else
-                            tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
+                        __syncwarp();
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -221,7 +223,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && !(PAIR && crank != 0)) {          // pair: only the leader issues (for both CTAs)
+        if (!(PAIR && crank != 0)) {                        // pair: only the leader issues (for both CTAs)
+            // The whole warp walks the schedule and waits; one elected lane issues (see elect_one() for why).
             constexpr uint32_t idesc = PAIR ? make_idesc_mn(2 * kTcBlockM, BN) : make_idesc(BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -236,23 +239,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (!mbar_wait(full0 + 8 * stage, phase, p.err_flag, 3)) { alive = false; break; }
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                    const uint32_t sb = sa + Cfg::kABytes;
+                    if (elect_one()) {
+                        const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
+                        const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
 #pragma unroll
-                    for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
-                        const uint64_t adesc = make_sw128_desc(sa + k * kTcUmmaK * 2);
-                        const uint64_t bdesc = make_sw128_desc(sb + k * kTcUmmaK * 2);
-                        if (PAIR) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {         // +32 bytes of K per MMA = +2 in the address field
+                            if (PAIR) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if (PAIR) umma_commit_2sm_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));  // frees the stage in both CTAs
+                        else if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));   // both CTAs' producers wait for both consumers
+                        else umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
+                        if (kb == num_kb - 1) {
+                            if (PAIR) umma_commit_2sm_mc(tfull0 + 8 * acc, static_cast<uint16_t>(3));       // both CTAs' epilogues
+                            else umma_commit(tfull0 + 8 * acc);      // accumulator ready for the epilogue
+                        }
                     }
-                    if (PAIR) umma_commit_2sm_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));  // frees the stage in both CTAs
-                    else if (CL == 2) umma_commit_mc(empty0 + 8 * stage, static_cast<uint16_t>(3));   // both CTAs' producers wait for both consumers
-                    else umma_commit(empty0 + 8 * stage);     // smem slot free once these MMAs retire
+                    __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (!alive) break;
-                if (PAIR) umma_commit_2sm_mc(tfull0 + 8 * acc, static_cast<uint16_t>(3));       // both CTAs' epilogues
-                else umma_commit(tfull0 + 8 * acc);      // accumulator ready for the epilogue
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -260,7 +266,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
     } else if (warp == 2) {
         // ===================== residual producer (TC_STORE_RES with a bf16 residual) =====================
-        if (MODE == TC_STORE_RES && has_res && lane == 0) {
+        if (MODE == TC_STORE_RES && has_res) {                 // whole warp + one elected lane per copy, as above
             uint32_t g = 0;
             bool alive = true;
             for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
@@ -270,9 +276,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     constexpr uint32_t R = Cfg::kNumR > 0 ? Cfg::kNumR : 1;
                     const uint32_t slot = g % R, use = g / R;
                     if (!mbar_wait(cempty0 + 8 * slot, (use & 1) ^ 1, p.err_flag, 5)) { alive = false; break; }
-                    mbar_arrive_expect_tx(cfull0 + 8 * slot, kChunkBytes);
-                    tma_load_2d(rbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
-                                m_tile * p.tile_rows);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(cfull0 + 8 * slot, kChunkBytes);
+                        tma_load_2d(rbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
+                                    m_tile * p.tile_rows);
+                    }
+                    __syncwarp();
                 }
             }
         }

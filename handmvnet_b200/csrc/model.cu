@@ -532,8 +532,8 @@ static int run_tail(hmv_handle* h, int tail, int units, cudaStream_t s) {
             const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
             for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += static_cast<double>(host[c * 16 + k]) / grid;
             fprintf(stderr, "[bt_prof] %s tiles/cta %.1f total %.0f | mma: t1empty %.0f full2 %.0f t2empty %.0f full3 %.0f | prod: empty %.0f y2ready %.0f | "
-                    "epi: t2full %.0f cfull %.0f t1full %.0f bulk %.0f namedbar %.0f | res: cempty %.0f (cycles, mean over CTAs)\n",
-                    T.name.c_str(), a[13], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+                    "epi: t2full %.0f cfull %.0f t1full %.0f bulk %.0f namedbar %.0f | res: cempty %.0f | mma warp: in the tcgen05.mma + commit issue blocks %.0f (+%.0f) (cycles, mean over CTAs)\n",
+                    T.name.c_str(), a[13], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[14], a[15]);
             ++printed;
         }
         return rc;

@@ -159,7 +159,7 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
         }
     } else if (warp == 12) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {   // the whole warp walks the schedule and waits; one elected lane issues (see elect_one() in tc_ptx.cuh for why)
             constexpr uint32_t idesc = make_idesc_mn(128, kC);
             const uint32_t ring_addr = smem_u32(ring), w_addr = smem_u32(wsm);
             uint32_t gq = 0, gt = 0;                       // pair counter at item start, running conv-row counter
@@ -178,21 +178,24 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
                     if (!alive) break;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * kC;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int r = 0; r < 7; ++r) {
-                        const uint32_t pq = gq + t + (r >> 1);
-                        const uint32_t row_addr = ring_addr + (pq % kRingSlots) * kPairBytes + (r & 1) * kRowPitch;
+                        for (int r = 0; r < 7; ++r) {
+                            const uint32_t pq = gq + t + (r >> 1);
+                            const uint32_t row_addr = ring_addr + (pq % kRingSlots) * kPairBytes + (r & 1) * kRowPitch;
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t adesc = make_nosw_desc(row_addr + kk * 32, 16, 128);
-                            const uint64_t bdesc = make_nosw_desc(w_addr + (r * 4 + kk * 2) * (kC * 16), kC * 16, 128);
-                            umma_f16(d_tmem, adesc, bdesc, idesc, (r | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const uint64_t adesc = make_nosw_desc(row_addr + kk * 32, 16, 128);
+                                const uint64_t bdesc = make_nosw_desc(w_addr + (r * 4 + kk * 2) * (kC * 16), kC * 16, 128);
+                                umma_f16(d_tmem, adesc, bdesc, idesc, (r | kk) != 0 ? 1u : 0u);
+                            }
                         }
+                        umma_commit(pempty0 + 8 * ((gq + t) % kRingSlots));          // pair t is not needed by later rows
+                        if (t == nrows - 1)
+                            for (int q = 1; q < 4; ++q) umma_commit(pempty0 + 8 * ((gq + t + q) % kRingSlots));
+                        umma_commit(afull0 + 8 * acc);
                     }
-                    umma_commit(pempty0 + 8 * ((gq + t) % kRingSlots));          // pair t is not needed by later rows
-                    if (t == nrows - 1)
-                        for (int q = 1; q < 4; ++q) umma_commit(pempty0 + 8 * ((gq + t + q) % kRingSlots));
-                    umma_commit(afull0 + 8 * acc);
+                    __syncwarp();
                 }
                 gq += nrows + 3;
             }

@@ -164,6 +164,24 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint32_t bar, uint16_t cta_ma
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
+// One lane of a fully converged warp.  The tcgen05.mma / commit issue sites sit inside `if (elect_one())` with the WHOLE warp
+// walking the surrounding loop: ptxas then knows a single thread is active and moves the operands to uniform registers
+// with plain R2URs (6 instructions per MMA).  Behind `if (lane == 0)` it emits a vote/broadcast loop around every MMA
+// (~17 instructions, ~100 cycles per MMA alone and 300 when an epilogue warp competes for the scheduler), which caps
+// an M = 128 MMA at ~100-166 cycles whatever N is (tools/mma_issue_bench.cu: 48 / 64 / 128 cycles for N = 64 / 128 / 256
+// once the issue path is lean).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
