@@ -75,11 +75,18 @@ class ClockSampler:
     def _run(self):
         try:
             import pynvml as nv
+            if os.environ.get("HMV_BENCH_SAMPLER_LATE", "0") == "1":
+                self._active.wait()                # (experiment) NVML is not even initialised before the timed steps are enqueued
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
             self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             mode = os.environ.get("HMV_BENCH_SAMPLER", "full")
+            # first calls outside the timed region (they run during the clock ramp): the first query of each kind is the slow one
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            if mode != "clock":
+                nv.nvmlDeviceGetPowerUsage(h)
+                get_reasons(h)
             while not self._stop.is_set():
                 if not self._active.wait(timeout=0.05):
                     continue
@@ -97,10 +104,10 @@ class ClockSampler:
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
-    # NVML queries from a second thread were measured to stall the thread that enqueues CUDA work for 50-140 ms every
-    # few runs (4 of 7 runs with the sampler, 0 of 3 without: profiles/r02/README.md), which empties the GPU queue in the
-    # middle of the timed region.  The sampler therefore runs only between resume() - called once all K timed steps
-    # are enqueued, i.e. while the GPU is still working through them - and pause() at the end of the region.
+    # The sampler queries only between resume() - called once all K timed steps are enqueued, i.e. while the GPU is
+    # still working through them - and pause() at the end of the region, so that it never competes with the thread
+    # that enqueues CUDA work.  (The 50-140 ms stalls once blamed on it were cudaGraphInstantiate inside the second
+    # timed step: see the warm-up comment in run_own.)
     def resume(self):
         self._active.set()
 
@@ -224,11 +231,18 @@ def run_own(args, lines):
     # not counted as one of the W warm-up steps
     # (time-bounded, so the number of iterations differs between ranks: no collective inside this loop)
     t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < args.ramp_seconds:
-        model(x, bbox, cam)
+    # The results are held the way the timed loop holds them (`out = step()` keeps step k's tensors alive while step
+    # k+1 allocates its own), so the two alternating sets of output buffers - and the library's pointer-keyed CUDA
+    # graphs for them, captured the second time a set is seen - exist before the timed region: in round 2 the second
+    # timed step was measured to spend 1-165 ms of host time in cudaGraphInstantiate, starving the GPU.
+    out = None
+    n_pre = 0
+    while time.perf_counter() - t_ramp < args.ramp_seconds or n_pre < 4:
+        out = model(x, bbox, cam)
         torch.cuda.synchronize(dev)
+        n_pre += 1
     for _ in range(args.warmup):
-        step()
+        out = step()
     barrier()
     launches0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,10 +255,13 @@ def run_own(args, lines):
     e0.record()
     marks[0].record()
     t_enq = time.perf_counter()
+    enq_t = [t_enq]
     for i in range(args.steps):
         out = step()
         marks[i + 1].record()
+        enq_t.append(time.perf_counter())
     enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / args.steps
+    enq_steps = sorted(((enq_t[i + 1] - enq_t[i]) * 1e3, i) for i in range(args.steps))[-3:]
     e1.record()
     sampler.resume()          # the steps are enqueued; the GPU executes them while the clocks are sampled
     barrier()
@@ -320,7 +337,8 @@ def run_own(args, lines):
         line = {
             "metric": (METRIC if views == 5 else METRIC_FMT.format(v=views)) + (" [HRNet-w40 backbone]" if args.backbone == "hrnet" else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms_mean,
-            "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms},
+            "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1], "cpu_enqueue": enqueue_ms,
+                        "cpu_enqueue_slowest": [{"step": i, "ms": round(ms, 3)} for ms, i in reversed(enq_steps)]},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{'HO3D' if views == 5 else 'DexYCB-style'}_HandMvNet{'_HR' if args.backbone == 'hrnet' else ''} release config, synthetic {views}-view B={B} per GPU, bf16, random-init weights",

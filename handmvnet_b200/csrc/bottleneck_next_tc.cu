@@ -51,12 +51,15 @@ constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
 #ifndef HMV_BN_PAIR_STAGES
 #define HMV_BN_PAIR_STAGES 6
 #endif
+#ifndef HMV_BN_DEFER
+#define HMV_BN_DEFER 0                                          // 1: a slot is released one slab store later (needs >= 6 slots)
+#endif
 constexpr int kBnSlots = HMV_BN_SLOTS;
 // one CTA per tile: T3 stage = A 16 KiB + W3 chunk 16 KiB, T1 stage = W1 K block 32 KiB.
 // CTA pair (cta_group::2, PAIR): a CTA holds its own A rows and HALF of every weight tile: T3 stage = 16 + 8 KiB, T1 stage = 16 KiB
 template <bool PAIR> struct BnGeo {
     static constexpr int kStageBytes = PAIR ? 24 * 1024 : 32 * 1024;
-    static constexpr int kStages = PAIR ? HMV_BN_PAIR_STAGES : HMV_BN_STAGES;
+    static constexpr int kStages = PAIR ? HMV_BN_PAIR_STAGES : (HMV_BN_SLOTS > 4 && HMV_BN_STAGES > 4 ? 4 : HMV_BN_STAGES);
     static constexpr int kSmemBytes = kStages * kStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -355,12 +358,24 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
         uint32_t g = static_cast<uint32_t>(team);            // this warp's running slot index (advances by 2)
         int pending = -1;                                    // lane 0: slot whose TMA store may still be reading smem
+        int pending_old = -1;                                // lane 0, HMV_BN_DEFER: the slot stored before `pending`
         bool alive = true;
         long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_bulk = 0, w_ldt = 0, w_math = 0, w_fence = 0, w_issue = 0, w_head = 0;
         const long long e_start = clock64();
 
         // The slab store issued a while ago has read shared memory: the slot may be overwritten (once its MMAs retired too).
         auto release_pending = [&]() {
+            if (HMV_BN_DEFER) {                              // all but the newest store have read their slabs
+                if (lane == 0) {
+                    if (pending_old >= 0) {
+                        if (PROF) { const long long t0 = clock64(); bulk_wait_read<1>(); w_bulk += clock64() - t0; } else bulk_wait_read<1>();
+                        mbar_arrive(sfree0 + 8 * pending_old);
+                    }
+                    pending_old = pending;
+                    pending = -1;
+                }
+                return;
+            }
             if (lane == 0 && pending >= 0) {
                 if (PROF) { const long long t0 = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - t0; } else bulk_wait_read<0>();
                 mbar_arrive(sfree0 + 8 * pending);
@@ -446,7 +461,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         m * kTcBlockM);
             }
         }
-        if (lane == 0 && pending >= 0) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
+        if (lane == 0 && (pending >= 0 || pending_old >= 0)) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
         if (PROF && p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 24;
             o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = 0; o[14] = w_bulk; o[16] = w_ldt;

@@ -438,7 +438,7 @@ static int build_tc(hmv_handle* h, Layer& L) {
     // 0.284 -> 0.250; short-K layers (K = 512 / 576: downsample, l3.0.conv1, QKV) get 5-10 % slower because the pair couples
     // two epilogues to one MMA issuer.  HMV_PAIR=0 disables, HMV_PAIR_MINK=<K> moves the threshold.
     static const bool pair_mma = [] { const char* e = getenv("HMV_PAIR"); return !(e && e[0] == '0'); }();
-    static const int pair_min_k = [] { const char* e = getenv("HMV_PAIR_MINK"); return e ? atoi(e) : 1024; }();
+    static const int pair_min_k = [] { const char* e = getenv("HMV_PAIR_MINK"); return e ? atoi(e) : 512; }();
     if (t.cluster == 2 && pair_mma && L.K >= pair_min_k && static_cast<int64_t>(L.max_units) * L.rows_per_unit() >= 65536) t.cluster = 4;
     if (tc_make_tmap_wgt(&t.tmB, L.w, L.K, L.n_alloc, t.cluster >= 2 ? L.bn / 2 : L.bn)) {
         set_error(std::string(get_error()) + " [B map of " + L.name + "]");
