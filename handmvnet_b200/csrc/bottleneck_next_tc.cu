@@ -51,8 +51,8 @@ constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
 #ifndef HMV_BN_PAIR_STAGES
 #define HMV_BN_PAIR_STAGES 6
 #endif
-#ifndef HMV_BN_DEFER
-#define HMV_BN_DEFER 0                                          // 1: a slot is released one slab store later (needs >= 6 slots)
+#ifndef HMV_BN_STORE_DEPTH
+#define HMV_BN_STORE_DEPTH 1                                    // slot stores the store warp keeps in flight beyond the newest
 #endif
 constexpr int kBnSlots = HMV_BN_SLOTS;
 // one CTA per tile: T3 stage = A 16 KiB + W3 chunk 16 KiB, T1 stage = W1 K block 32 KiB.
@@ -102,9 +102,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 output [rows, 256], load box {64, 128}
                        const __grid_constant__ CUtensorMap tmW3,   // [1024, 256], box {64, 128}  
                        const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 1024], load box {64, 128}
-                       const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 32}
+                       const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 1024], store box {64, 128}
                        const __grid_constant__ CUtensorMap tmW1,   // next conv1 weights [256, 1024], box {64, 256}  
-                       const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 32}
+                       const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 128}
                        const __grid_constant__ BnParams p,
                        const __grid_constant__ BiasBank bank) {            // conv3 biases [0, 1024), next conv1 biases [1024, 1280)
     constexpr int kBnStages = BnGeo<PAIR>::kStages;            // (shadow the single-CTA constants)
@@ -122,7 +122,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
     const uint32_t sres0 = t1empty + 8;                       // [slots] residual landed / slot handed to the epilogue
     const uint32_t aready0 = sres0 + 8 * kBnSlots;            // [slots] finished block-output chunk is in the slot
     const uint32_t sfree0 = aready0 + 8 * kBnSlots;           // [slots] store has read the slot and its MMAs retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBnStages + 6 + 3 * kBnSlots);
+    const uint32_t stready0 = sfree0 + 8 * kBnSlots;          // [slots] this CTA's four slabs of the slot are written: the store warp may store it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBnStages + 6 + 4 * kBnSlots);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t slots_base = smem_u32(slots);
 
@@ -151,7 +152,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         for (int i = 0; i < kBnSlots; ++i) {
             mbar_init(sres0 + 8 * i, 1);
             mbar_init(aready0 + 8 * i, 4 * kCtas);           // the four slab warps of the team that handles the slot (in both CTAs of a pair)
-            mbar_init(sfree0 + 8 * i, 5);                   // 4 slab-store issuers + the MMA commit (conv3 slots) / the slot producer (conv1 slots)
+            mbar_init(sfree0 + 8 * i, 2);                   // the store warp + the MMA commit (conv3 slots) / the slot producer (conv1 slots)
+            mbar_init(stready0 + 8 * i, 4);                 // the four slab warps of the owning team (this CTA's)
         }
         fence_barrier_init();
     }
@@ -347,6 +349,37 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             if (PROF && p.prof && lane == 0) p.prof[blockIdx.x * 24 + 8] = w_sf;
         }
         __syncwarp();
+    } else if (warp == 3) {
+        // ===================== store warp: finished slots -> global memory =====================
+        // One TMA store per 16 KiB slot, issued here instead of by the epilogue warps: waiting until a store has read its
+        // slot (before the slot goes back to the residual prefetcher) cost every epilogue warp ~750 cycles per slot -
+        // a quarter of its time - and the epilogue is what bounds this kernel once the MMAs are issued leanly.
+        {
+            uint32_t g = 0;
+            bool alive = true;
+            long long w_st = 0, w_rd = 0;
+            for (int i = 0; i < n_i && alive; ++i) {
+                const int m = tile_of(i);
+                for (int j = 0; j < kBnSlotsPerTile && alive; ++j, ++g) {
+                    const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
+                    if (!bn_wait<PROF>(stready0 + 8 * slot, use & 1u, p.err_flag, 62, w_st)) { alive = false; break; }
+                    if (elect_one()) {                     // (elect.sync picks the same lane every time: the bulk groups are its own)
+                        if (j < 2 * kBnNch) tma_store_2d(&tmOut, slots_base + slot * kBnSlotBytes, j * kBnSlotCols, m * kTcBlockM);
+                        else tma_store_2d(&tmY1, slots_base + slot * kBnSlotBytes, (j - 2 * kBnNch) * kBnSlotCols, m * kTcBlockM);
+                        bulk_commit();
+                        if (g >= HMV_BN_STORE_DEPTH) {     // the store issued HMV_BN_STORE_DEPTH slots ago has read its slot
+                            if (PROF) { const long long t0 = clock64(); bulk_wait_read<HMV_BN_STORE_DEPTH>(); w_rd += clock64() - t0; }
+                            else bulk_wait_read<HMV_BN_STORE_DEPTH>();
+                            mbar_arrive(sfree0 + 8 * ((g - HMV_BN_STORE_DEPTH) % kBnSlots));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) bulk_wait_read<0>();            // staged data must stay valid until every store has read it
+            __syncwarp();
+            if (PROF && p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 13] = w_st; p.prof[blockIdx.x * 24 + 14] = w_rd; }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue: 2 teams x 4 warps; a warp owns one 32-row slab (TMEM lane quarter) of a whole 64-column slot ==========
         // Team t takes the slots with running index g = t (mod 2): the two 64-column halves of a conv3 chunk / alternate
@@ -357,33 +390,11 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const uint32_t slab_off = quarter * (32 * 128) + lane * 128;
         uint32_t g = static_cast<uint32_t>(team);            // this warp's running slot index (advances by 2)
-        int pending = -1;                                    // lane 0: slot whose TMA store may still be reading smem
-        int pending_old = -1;                                // lane 0, HMV_BN_DEFER: the slot stored before `pending`
         bool alive = true;
-        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_bulk = 0, w_ldt = 0, w_math = 0, w_fence = 0, w_issue = 0, w_head = 0;
+        long long w_sres = 0, w_t3f = 0, w_t1f = 0, w_ldt = 0, w_math = 0, w_fence = 0, w_issue = 0, w_head = 0;
         const long long e_start = clock64();
 
-        // The slab store issued a while ago has read shared memory: the slot may be overwritten (once its MMAs retired too).
-        auto release_pending = [&]() {
-            if (HMV_BN_DEFER) {                              // all but the newest store have read their slabs
-                if (lane == 0) {
-                    if (pending_old >= 0) {
-                        if (PROF) { const long long t0 = clock64(); bulk_wait_read<1>(); w_bulk += clock64() - t0; } else bulk_wait_read<1>();
-                        mbar_arrive(sfree0 + 8 * pending_old);
-                    }
-                    pending_old = pending;
-                    pending = -1;
-                }
-                return;
-            }
-            if (lane == 0 && pending >= 0) {
-                if (PROF) { const long long t0 = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - t0; } else bulk_wait_read<0>();
-                mbar_arrive(sfree0 + 8 * pending);
-                pending = -1;
-            }
-        };
-
-        auto do_slot = [&](uint32_t tcol, int bias_off, bool is_conv3, uint32_t release_bar, const CUtensorMap* tm_out, int col, int row) {
+        auto do_slot = [&](uint32_t tcol, int bias_off, bool is_conv3, uint32_t release_bar) {
             const uint32_t slot = g % kBnSlots, use = g / kBnSlots;
             uint8_t* srow = slots + slot * kBnSlotBytes + slab_off;
             long long tp = PROF ? clock64() : 0;
@@ -429,9 +440,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             if (PROF) { const long long t0 = clock64(); w_fence += t0 - tp; tp = t0; }
             if (lane == 0) {
                 arrive_mma(aready0 + 8 * slot);              // every slot use (conv1 slots too: keeps the barrier's phase == use count)
-                tma_store_2d(tm_out, slots_base + slot * kBnSlotBytes + quarter * (32 * 128), col, row + quarter * 32);
-                bulk_commit();
-                pending = static_cast<int>(slot);
+                mbar_arrive(stready0 + 8 * slot);            // this warp's slab is in the slot: the store warp stores it once all four are
             }
             __syncwarp();
             if (PROF) { w_issue += clock64() - tp; }
@@ -443,28 +452,22 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             const int m = tile_of(i);
             for (int c = 0; c < kBnNch && alive; ++c, ++q3) {
                 const uint32_t s = q3 & 1u;
-                release_pending();                           // the slot goes back to the residual prefetcher ahead of its next use
                 if (!bn_wait<PROF>(t3full0 + 8 * s, (q3 >> 1) & 1u, p.err_flag, 60, w_t3f)) { alive = false; break; }
                 tc_fence_after();
-                do_slot(kBnP + s * kBnChunk + team * kBnSlotCols, c * kBnChunk + team * kBnSlotCols, true, t3empty0 + 8 * s, &tmOut,
-                        c * kBnChunk + team * kBnSlotCols, m * kTcBlockM);
+                do_slot(kBnP + s * kBnChunk + team * kBnSlotCols, c * kBnChunk + team * kBnSlotCols, true, t3empty0 + 8 * s);
             }
             if (!alive) break;
-            release_pending();
             if (!bn_wait<PROF>(t1full, static_cast<uint32_t>(i) & 1u, p.err_flag, 61, w_t1f)) { alive = false; break; }
             tc_fence_after();
 #pragma unroll 1
             for (int k = 0; k < kBnP / kBnSlotCols / 2 && alive; ++k) {
-                if (k > 0) release_pending();
                 const int cc = 2 * k + team;
-                do_slot(cc * kBnSlotCols, kBnBias1Off + cc * kBnSlotCols, false, k == kBnP / kBnSlotCols / 2 - 1 ? t1empty : 0u, &tmY1, cc * kBnSlotCols,
-                        m * kTcBlockM);
+                do_slot(cc * kBnSlotCols, kBnBias1Off + cc * kBnSlotCols, false, k == kBnP / kBnSlotCols / 2 - 1 ? t1empty : 0u);
             }
         }
-        if (lane == 0 && (pending >= 0 || pending_old >= 0)) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
         if (PROF && p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 24;
-            o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[13] = 0; o[14] = w_bulk; o[16] = w_ldt;
+            o[9] = clock64() - e_start; o[10] = w_t3f; o[11] = w_sres; o[12] = w_t1f; o[16] = w_ldt;
             o[17] = w_head; o[18] = w_math; o[19] = w_fence; o[20] = w_issue;
         }
         __syncwarp();

@@ -576,7 +576,7 @@ static int run_seam(hmv_handle* h, int seam, int units, cudaStream_t s) {
             const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
             for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) a[k] += static_cast<double>(host[c * 24 + k]) / grid;
             fprintf(stderr, "[bn_prof] %s tiles/cta %.1f | mma total %.0f: t3empty %.0f full3 %.0f t1empty %.0f aready %.0f full1 %.0f | prod: empty3 %.0f empty1 %.0f | "
-                    "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f namedbar %.0f bulk %.0f tmem_ld %.0f | per-slot phases (incl. the waits above): head %.0f ldwait %.0f math+sts %.0f fence %.0f issue %.0f (cycles, mean over CTAs)\n",
+                    "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f | store warp: waits for slabs %.0f, for store reads %.0f | tmem_ld %.0f | per-slot phases (incl. the waits above): head %.0f ldwait %.0f math+sts %.0f fence %.0f issue %.0f (cycles, mean over CTAs)\n",
                     S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16],
                     a[17], a[16], a[18], a[19], a[20]);
             ++printed;
@@ -767,7 +767,12 @@ static int add_seam(hmv_handle* h, const std::string& name, int l3, int l1) {
         set_error(std::string(get_error()) + " [fused-seam maps of " + name + "]");
         return 1;
     }
-    b.tmRes = A.tc.tmR; b.tmOut = A.tc.tmC; b.tmY1 = B.tc.tmC;
+    b.tmRes = A.tc.tmR;
+    // whole-slot stores (128 rows x 64 columns) issued by the kernel's store warp
+    if (tc_make_tmap_out(&b.tmOut, A.ep.out, A.ep.ldc, rows, 128) || tc_make_tmap_out(&b.tmY1, B.ep.out, B.ep.ldc, rows, 128)) {
+        set_error(std::string(get_error()) + " [fused-seam store maps of " + name + "]");
+        return 1;
+    }
     memset(&b.bank, 0, sizeof(b.bank));
     memcpy(b.bank.v, A.bias_host.data(), sizeof(float) * 1024);
     memcpy(b.bank.v + kBnBias1Off, B.bias_host.data(), sizeof(float) * 256);
