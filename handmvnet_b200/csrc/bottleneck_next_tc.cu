@@ -37,39 +37,49 @@ constexpr int kBnNch = kBnN3 / kBnChunk;                        // 8 chunks per 
 constexpr int kBnKb3 = kBnP / kTcBlockK;                        // 4 K blocks per T3
 constexpr int kBnSlotCols = 64;
 constexpr int kBnSlotBytes = kTcBlockM * kBnSlotCols * 2;       // 16 KiB
-// (ring depth is the first-order knob: 5 stages + 4 slots 0.40 ms, 4 + 6 0.49, 3 + 8 0.55 per B=64 launch, with either lag;
-//  the macros exist for that sweep, tools/gpu_r02_variants.sh)
+// Shared memory of a CTA: the tile's conv2 output Y2 (the A operand of all 8 conv3 chunks, 4 K blocks x 16 KiB, loaded once
+// per tile), a ring of weight stages, and the staging slots.  A stage holds two K blocks of one conv3 chunk's weights
+// (T3: 8 MMAs) or one K block of the next conv1's weights (T1: 4 MMAs) - 512 tensor cycles either way.
+//   one CTA per tile:  stage 32 KiB (2 x [128 x 64] of W3 / [256 x 64] of W1), 3 stages, 4 slots
+//   CTA pair (cta_group::2, PAIR): a CTA holds HALF of every weight tile: stage 16 KiB, 4 stages, 6 slots
+// (Until round 2 the A operand travelled through the ring with every chunk's weights - 24-32 KiB stages, 5-6 of them and
+//  only 4 slots: the slots, each used 5 times per tile with a residual prefetch, the epilogue, the next conv1's MMAs and a
+//  store in every cycle, were what bounded the kernel once the MMA issue path was lean.)
 #ifndef HMV_BN_SLOTS
 #define HMV_BN_SLOTS 4
 #endif
 #ifndef HMV_BN_STAGES
-#define HMV_BN_STAGES 5
+#define HMV_BN_STAGES 3
+#endif
+#ifndef HMV_BN_PAIR_SLOTS
+#define HMV_BN_PAIR_SLOTS 6
+#endif
+#ifndef HMV_BN_PAIR_STAGES
+#define HMV_BN_PAIR_STAGES 4
 #endif
 #ifndef HMV_BN_LAG
 #define HMV_BN_LAG 1
 #endif
-#ifndef HMV_BN_PAIR_STAGES
-#define HMV_BN_PAIR_STAGES 6
+#ifndef HMV_BN_PAIR_LAG
+#define HMV_BN_PAIR_LAG 2                                       // (4 stages + 6 slots: lag 1 0.355 ms, lag 2 0.344; 6 + 4, lag 1: 0.348)
 #endif
 #ifndef HMV_BN_STORE_DEPTH
 #define HMV_BN_STORE_DEPTH 1                                    // slot stores the store warp keeps in flight beyond the newest
 #endif
-constexpr int kBnSlots = HMV_BN_SLOTS;
-// one CTA per tile: T3 stage = A 16 KiB + W3 chunk 16 KiB, T1 stage = W1 K block 32 KiB.
-// CTA pair (cta_group::2, PAIR): a CTA holds its own A rows and HALF of every weight tile: T3 stage = 16 + 8 KiB, T1 stage = 16 KiB
+constexpr int kBnY2Bytes = kTcBlockM * kBnP * 2;                // 64 KiB: 4 K blocks of [128 rows x 64] bf16, 128B swizzle
 template <bool PAIR> struct BnGeo {
-    static constexpr int kStageBytes = PAIR ? 24 * 1024 : 32 * 1024;
-    static constexpr int kStages = PAIR ? HMV_BN_PAIR_STAGES : (HMV_BN_SLOTS > 4 && HMV_BN_STAGES > 4 ? 4 : HMV_BN_STAGES);
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBnSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int kHalfBytes = PAIR ? 8 * 1024 : 16 * 1024;          // one K block of a conv3 chunk's weights
+    static constexpr int kStageBytes = 2 * kHalfBytes;
+    static constexpr int kStages = PAIR ? HMV_BN_PAIR_STAGES : HMV_BN_STAGES;
+    static constexpr int kSlots = PAIR ? HMV_BN_PAIR_SLOTS : HMV_BN_SLOTS;
+    static constexpr int kLag = PAIR ? HMV_BN_PAIR_LAG : HMV_BN_LAG;      // T1(c - kLag) follows T3(c): gives the epilogue of chunk c - kLag time to finish
+    static constexpr int kSmemBytes = kBnY2Bytes + kStages * kStageBytes + kSlots * kBnSlotBytes + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(kStages >= 2 && kSlots >= 4 && kSlots % 2 == 0, "two epilogue teams alternate over the slots");
 };
-constexpr int kBnStageBytes = BnGeo<false>::kStageBytes;
-constexpr int kBnStages = BnGeo<false>::kStages;
-constexpr int kBnLag = HMV_BN_LAG;                                        // T1(c - kBnLag) follows T3(c): the epilogue of chunk c-2 is long done by then
 constexpr int kBnSlotsPerTile = 2 * kBnNch + kBnP / kBnSlotCols; // 16 conv3 slots + 4 conv1 slots
-constexpr int kBnSmemBytes = BnGeo<false>::kSmemBytes;
 
-template <typename F3, typename F1>
+template <int kBnLag, typename F3, typename F1>
 __device__ __forceinline__ bool bn_tile_schedule(F3&& t3, F1&& t1) {
     for (int c = 0; c < kBnNch; ++c) {
         if (!t3(c)) return false;
@@ -107,11 +117,14 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                        const __grid_constant__ CUtensorMap tmY1,   // next conv1 output [rows, 256], store box {64, 128}
                        const __grid_constant__ BnParams p,
                        const __grid_constant__ BiasBank bank) {            // conv3 biases [0, 1024), next conv1 biases [1024, 1280)
-    constexpr int kBnStages = BnGeo<PAIR>::kStages;            // (shadow the single-CTA constants)
+    constexpr int kBnStages = BnGeo<PAIR>::kStages;
     constexpr int kBnStageBytes = BnGeo<PAIR>::kStageBytes;
+    constexpr int kBnHalfBytes = BnGeo<PAIR>::kHalfBytes;
+    constexpr int kBnSlots = BnGeo<PAIR>::kSlots;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* slots = smem + kBnStages * kBnStageBytes;
+    uint8_t* ring = smem + kBnY2Bytes;                        // [0, 64 KiB): the tile's Y2
+    uint8_t* slots = ring + kBnStages * kBnStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(slots + kBnSlots * kBnSlotBytes);
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = full0 + 8 * kBnStages;
@@ -119,12 +132,15 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
     const uint32_t t3empty0 = t3full0 + 16;
     const uint32_t t1full = t3empty0 + 16;
     const uint32_t t1empty = t1full + 8;
-    const uint32_t sres0 = t1empty + 8;                       // [slots] residual landed / slot handed to the epilogue
+    const uint32_t y2full = t1empty + 8;                      // the tile's Y2 has landed (in both CTAs of a pair)
+    const uint32_t y2empty = y2full + 8;                      // the tile's last conv3 MMA has retired: Y2 may be overwritten
+    const uint32_t sres0 = y2empty + 8;                       // [slots] residual landed / slot handed to the epilogue
     const uint32_t aready0 = sres0 + 8 * kBnSlots;            // [slots] finished block-output chunk is in the slot
     const uint32_t sfree0 = aready0 + 8 * kBnSlots;           // [slots] store has read the slot and its MMAs retired
     const uint32_t stready0 = sfree0 + 8 * kBnSlots;          // [slots] this CTA's four slabs of the slot are written: the store warp may store it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBnStages + 6 + 4 * kBnSlots);
-    const uint32_t smem_base = smem_u32(smem);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBnStages + 8 + 4 * kBnSlots);
+    const uint32_t y2_base = smem_u32(smem);
+    const uint32_t smem_base = smem_u32(ring);                // weight ring
     const uint32_t slots_base = smem_u32(slots);
 
     const int warp = threadIdx.x >> 5;
@@ -149,6 +165,8 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         }
         mbar_init(t1full, 1);
         mbar_init(t1empty, 8 * kCtas);
+        mbar_init(y2full, 1);
+        mbar_init(y2empty, 1);
         for (int i = 0; i < kBnSlots; ++i) {
             mbar_init(sres0 + 8 * i, 1);
             mbar_init(aready0 + 8 * i, 4 * kCtas);           // the four slab warps of the team that handles the slot (in both CTAs of a pair)
@@ -189,25 +207,41 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
         {   // the whole warp walks the schedule and waits; one elected lane issues the copies (see elect_one() in tc_ptx.cuh)
             int stage = 0;
             uint32_t phase = 0;
-            long long w_e3 = 0, w_e1 = 0;
+            long long w_e3 = 0, w_e1 = 0, w_y2e = 0;
             for (int i = 0; i < n_i; ++i) {
                 const int m = tile_of(i);
-                const bool ok = bn_tile_schedule(
+                // this tile's Y2: once the previous tile's last conv3 MMA has retired
+                if (!bn_wait<PROF>(y2empty, (static_cast<uint32_t>(i) & 1u) ^ 1u, p.err_flag, 63, w_y2e)) break;
+                if (elect_one()) {
+                    if (PAIR) {                    // both CTAs' bytes are counted on the LEADER's barrier, which only the leader arms
+                        const uint32_t lfb = crank == 0 ? y2full : mapa_u32(y2full, 0);
+                        if (crank == 0) mbar_arrive_expect_tx(y2full, 2u * kBnY2Bytes);
+#pragma unroll
+                        for (int kb = 0; kb < kBnKb3; ++kb) tma_load_2d_2sm(y2_base + kb * 16384, &tmY2, lfb, kb * kTcBlockK, m * kTcBlockM);
+                    } else {
+                        mbar_arrive_expect_tx(y2full, kBnY2Bytes);
+#pragma unroll
+                        for (int kb = 0; kb < kBnKb3; ++kb) tma_load_2d(y2_base + kb * 16384, &tmY2, y2full, kb * kTcBlockK, m * kTcBlockM);
+                    }
+                }
+                __syncwarp();
+                const bool ok = bn_tile_schedule<BnGeo<PAIR>::kLag>(
                     [&](int c) {
-                        for (int kb = 0; kb < kBnKb3; ++kb) {
+                        for (int s2 = 0; s2 < kBnKb3 / 2; ++s2) {          // a stage = two K blocks of this chunk's weights
                             if (!bn_wait<PROF>(empty0 + 8 * stage, phase ^ 1, p.err_flag, 51, w_e3)) return false;
                             if (elect_one()) {
                                 const uint32_t fb = full0 + 8 * stage;
-                                const uint32_t sa = smem_base + stage * kBnStageBytes;
-                                if (PAIR) {        // own A rows + this CTA's 64 of the chunk's 128 weight rows; bytes counted on the leader
+                                const uint32_t sb = smem_base + stage * kBnStageBytes;
+                                if (PAIR) {        // this CTA's 64 of the chunk's 128 weight rows; bytes counted on the leader
                                     const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
-                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (16384u + 8192u));
-                                    tma_load_2d_2sm(sa, &tmY2, lfb, kb * kTcBlockK, m * kTcBlockM);
-                                    tma_load_2d_2sm(sa + 16384, &tmW3, lfb, kb * kTcBlockK, c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2));
+                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * kBnStageBytes);
+#pragma unroll
+                                    for (int hb = 0; hb < 2; ++hb)
+                                        tma_load_2d_2sm(sb + hb * kBnHalfBytes, &tmW3, lfb, (2 * s2 + hb) * kTcBlockK, c * kBnChunk + static_cast<int>(crank) * (kBnChunk / 2));
                                 } else {
                                     mbar_arrive_expect_tx(fb, kBnStageBytes);
-                                    tma_load_2d(sa, &tmY2, fb, kb * kTcBlockK, m * kTcBlockM);
-                                    tma_load_2d(sa + kBnStageBytes / 2, &tmW3, fb, kb * kTcBlockK, c * kBnChunk);
+#pragma unroll
+                                    for (int hb = 0; hb < 2; ++hb) tma_load_2d(sb + hb * kBnHalfBytes, &tmW3, fb, (2 * s2 + hb) * kTcBlockK, c * kBnChunk);
                                 }
                             }
                             __syncwarp();
@@ -222,7 +256,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                                 const uint32_t fb = full0 + 8 * stage;
                                 if (PAIR) {        // this CTA's 128 of the 256 weight rows of the K block
                                     const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
-                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * 16384u);
+                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * kBnStageBytes);
                                     tma_load_2d_2sm(smem_base + stage * kBnStageBytes, &tmW1, lfb, (2 * c + j) * kTcBlockK, static_cast<int>(crank) * (kBnP / 2));
                                 } else {
                                     mbar_arrive_expect_tx(fb, kBnStageBytes);
@@ -236,7 +270,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                     });
                 if (!ok) break;
             }
-            if (PROF && p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 6] = w_e3; p.prof[blockIdx.x * 24 + 7] = w_e1; }
+            if (PROF && p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 6] = w_e3; p.prof[blockIdx.x * 24 + 7] = w_e1; p.prof[blockIdx.x * 24 + 22] = w_y2e; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -263,27 +297,34 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q3 = 0;                                 // running conv3 chunk counter (TMEM slot = q3 & 1)
-            long long w_t3e = 0, w_f3 = 0, w_t1e = 0, w_ar = 0, w_f1 = 0;
+            long long w_t3e = 0, w_f3 = 0, w_t1e = 0, w_ar = 0, w_f1 = 0, w_y2f = 0;
             const long long t_start = clock64();
             for (int i = 0; i < n_i; ++i) {
                 const uint32_t gbase = static_cast<uint32_t>(i) * kBnSlotsPerTile;
-                const bool ok = bn_tile_schedule(
-                    [&](int) {
+                const bool ok = bn_tile_schedule<BnGeo<PAIR>::kLag>(
+                    [&](int c) {
                         const uint32_t s = q3 & 1u, use = q3 >> 1;
                         if (!wait_epi(t3empty0 + 8 * s, (use & 1u) ^ 1u, 53, w_t3e)) return false;
+                        if (c == 0 && !bn_wait<PROF>(y2full, static_cast<uint32_t>(i) & 1u, p.err_flag, 64, w_y2f)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBnP + s * kBnChunk;
-                        for (int kb = 0; kb < kBnKb3; ++kb) {
+                        for (int s2 = 0; s2 < kBnKb3 / 2; ++s2) {
                             if (!bn_wait<PROF>(full0 + 8 * stage, phase, p.err_flag, 54, w_f3)) return false;
                             tc_fence_after();
                             if (elect_one()) {
-                                const uint64_t adesc = make_sw128_desc(smem_base + stage * kBnStageBytes);
-                                const uint64_t bdesc = make_sw128_desc(smem_base + stage * kBnStageBytes + 16384);
 #pragma unroll
-                                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
-                                    mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb | k) != 0 ? 1u : 0u);
+                                for (int hb = 0; hb < 2; ++hb) {
+                                    const uint64_t adesc = make_sw128_desc(y2_base + (2 * s2 + hb) * 16384);          // resident Y2, K block 2*s2+hb
+                                    const uint64_t bdesc = make_sw128_desc(smem_base + stage * kBnStageBytes + hb * kBnHalfBytes);
+#pragma unroll
+                                    for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)   // +32 bytes of K per MMA = +2 in the address field
+                                        mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (s2 | hb | k) != 0 ? 1u : 0u);
+                                }
                                 commit(empty0 + 8 * stage);
-                                if (kb == kBnKb3 - 1) commit(t3full0 + 8 * s);
+                                if (s2 == kBnKb3 / 2 - 1) {
+                                    commit(t3full0 + 8 * s);
+                                    if (c == kBnNch - 1) commit(y2empty);                  // the tile's Y2 is no longer needed (both CTAs of a pair)
+                                }
                             }
                             __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
@@ -319,7 +360,7 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
             }
             if (PROF && p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 24;
-                o[0] = clock64() - t_start; o[1] = w_t3e; o[2] = w_f3; o[3] = w_t1e; o[4] = w_ar; o[5] = w_f1; o[15] = n_i;
+                o[0] = clock64() - t_start; o[1] = w_t3e; o[2] = w_f3; o[3] = w_t1e; o[4] = w_ar; o[5] = w_f1; o[15] = n_i; o[21] = w_y2f;
             }
         }
         __syncwarp();

@@ -575,9 +575,9 @@ static int run_seam(hmv_handle* h, int seam, int units, cudaStream_t s) {
             double a[24] = {0};
             const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
             for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) a[k] += static_cast<double>(host[c * 24 + k]) / grid;
-            fprintf(stderr, "[bn_prof] %s tiles/cta %.1f | mma total %.0f: t3empty %.0f full3 %.0f t1empty %.0f aready %.0f full1 %.0f | prod: empty3 %.0f empty1 %.0f | "
+            fprintf(stderr, "[bn_prof] %s tiles/cta %.1f | mma total %.0f: t3empty %.0f full3 %.0f t1empty %.0f aready %.0f full1 %.0f y2full %.0f | prod: empty3 %.0f empty1 %.0f y2empty %.0f | "
                     "slots: sfree %.0f | epi total %.0f: t3full %.0f sres %.0f t1full %.0f | store warp: waits for slabs %.0f, for store reads %.0f | tmem_ld %.0f | per-slot phases (incl. the waits above): head %.0f ldwait %.0f math+sts %.0f fence %.0f issue %.0f (cycles, mean over CTAs)\n",
-                    S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16],
+                    S.name.c_str(), a[15], a[0], a[1], a[2], a[3], a[4], a[5], a[21], a[6], a[7], a[22], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[16],
                     a[17], a[16], a[18], a[19], a[20]);
             ++printed;
         }

@@ -13,4 +13,4 @@ g = lambda k: cl[k]["ms_per_launch"] if k in cl else float("nan")
 print("value %.0f step median %.3f max %.3f | seam %.4f  l1 tail %.4f  l2 tail %.4f  l3.conv2 %.4f" % (d["value"], d["step_ms"]["median"], d["step_ms"]["max"], g("layer3.x.conv3+next.conv1"), g("layer1.x.conv2+conv3"), g("layer2.x.conv2+conv3"), g("layer3.x.conv2")))
 PY
 done
-HMV_BN_PROF=1 timeout 300 python bench.py --steps 3 --warmup 3 --ramp-seconds 0.5 --no-e2e --no-eager --no-latency --no-cpu-baseline --no-clocks 2> gpurun_out/bn_prof_s.err > /dev/null; grep bn_prof gpurun_out/bn_prof_s.err | head -2 | cut -c1-800
+HMV_BT_PROF=1 timeout 300 python bench.py --steps 3 --warmup 3 --ramp-seconds 0.5 --no-e2e --no-eager --no-latency --no-cpu-baseline --no-clocks 2> gpurun_out/bt_prof_s.err > /dev/null; grep bt_prof gpurun_out/bt_prof_s.err | head -5 | cut -c1-600
