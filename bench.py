@@ -399,12 +399,13 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
     classes = {}
     with open(csv_path) as f:
         for row in csv.DictReader(f):
-            c = classes.setdefault(kernel_class(row["layer"]), {"n": 0, "ms": 0.0, "gflop": 0.0, "mbytes": 0.0, "mmas": 0.0})
+            c = classes.setdefault(kernel_class(row["layer"]), {"n": 0, "ms": 0.0, "gflop": 0.0, "mbytes": 0.0, "mmas": 0.0, "mma_cycles": 0.0})
             c["n"] += 1
             c["ms"] += float(row["ms"])
             c["gflop"] += float(row["gflop"])
             c["mbytes"] += float(row["mbytes"])
             c["mmas"] += float(row.get("mmas") or 0.0)
+            c["mma_cycles"] += float(row.get("mma_cycles") or 0.0)
     tpeak, hpeak = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
     traffic = load_traffic(views, batch, micro_batch)
     out = []
@@ -419,14 +420,13 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
                "peak": tpeak if bound == "tensor" else hpeak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                "frac": max(t_tensor, t_hbm) / ms_l, "tflops": c["gflop"] / c["ms"], "gbs": c["mbytes"] / c["ms"],
                "algorithmic_mbytes_per_launch": c["mbytes"] / c["n"], "gflop_per_launch": c["gflop"] / c["n"]}
-        if c["mmas"] > 0:
-            # tensor-ISSUE floor: an M=128 tcgen05.mma from shared memory costs ~128 cycles whatever N <= 256 is, so a layer
-            # with N = 64 / 128 cannot reach the FLOP roofline; this is what bounds the fused layer1 / layer2 / seam kernels
-            import math
+        if c["mma_cycles"] > 0:
+            # tensor-pipe floor at the shapes the kernel issues: an MMA over 128 rows x N columns x K = 16 takes max(N / 2, 48)
+            # cycles (tools/mma_issue_bench.cu), so layers with N = 64 / 128 cannot reach the FLOP roofline
             mhz = sm_mhz or 1550.0
             rec["mma_per_launch"] = c["mmas"] / c["n"]
-            rec["issue_floor_ms"] = math.ceil(rec["mma_per_launch"] / num_sms) * 128.0 / (mhz * 1e3)
-            rec["frac_issue"] = rec["issue_floor_ms"] / ms_l
+            rec["tensor_shape_floor_ms"] = c["mma_cycles"] / c["n"] / num_sms / (mhz * 1e3)
+            rec["frac_tensor_shape"] = rec["tensor_shape_floor_ms"] / ms_l
         out.append(rec)
     out.sort(key=lambda r: -r["ms_per_step"])
     top = dict(out[0]) if out else {}
@@ -454,9 +454,10 @@ def roofline_report(csv_path, steps, step_ms, peaks, views, batch, micro_batch, 
                      "end_to_end_model_tflops": model_tflops}
     top["phase_ms_per_step"] = phases
     top["classes"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
-                       if k in ("kernel", "launches_per_step", "ms_per_launch", "ms_per_step", "bound", "frac", "tflops", "gbs", "issue_floor_ms", "frac_issue")} for r in out]
-    top["issue_floor_note"] = ("issue_floor_ms = ceil(tcgen05.mma count / SMs) x 128 cycles at the SM clock sampled during the timed region: the "
-                               "shape-limited tensor floor of a launch (an M=128 MMA costs the same for N = 64, 128 or 256)")
+                       if k in ("kernel", "launches_per_step", "ms_per_launch", "ms_per_step", "bound", "frac", "tflops", "gbs", "tensor_shape_floor_ms", "frac_tensor_shape")} for r in out]
+    top["tensor_shape_floor_note"] = ("tensor_shape_floor_ms = sum over the launch's tcgen05.mma of max(N / 2, 48) cycles, / SMs, at the SM clock "
+                                      "sampled during the timed region: what the tensor pipe needs at the N the layer allows (measured: "
+                                      "tools/mma_issue_bench.cu); `frac` stays the FLOP / HBM roofline fraction")
     return top
 
 

@@ -2259,7 +2259,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
     HMV_CUDA(cudaDeviceSynchronize());
     double ms = 0.0, fl = 0.0;
     FILE* f = csv_path ? fopen(csv_path, "w") : nullptr;
-    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops,mbytes,mmas\n");
+    if (f) fprintf(f, "layer,M,N,K_real,bn,ms,gflop,tflops,mbytes,mmas,mma_cycles\n");
     for (auto& r : h->prof) {
         float t = 0.f;
         cudaEventElapsedTime(&t, r.e0, r.e1);
@@ -2276,12 +2276,17 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         std::string name = L.name;
         int ncol = L.cout;
         double kcol = kreal;
-        // tcgen05.mma instructions (M = 128, K = 16) the launch issues: an MMA costs about the same whatever N <= 256 is
-        // (A-operand fetch), so this count x ~128 cycles / SMs is the launch's tensor-issue floor
+        // tcgen05.mma instructions (128 rows per SM, K = 16) the launch issues and the tensor-pipe cycles they take at the
+        // measured rate: max(N / 2, 48) cycles for an N-column MMA (tools/mma_issue_bench.cu: 48 / 64 / 96 / 128 cycles for
+        // N = 64 / 128 / 192 / 256, one CTA or a cta_group::2 pair alike) - the shape-limited tensor floor of the launch
+        auto mma_cyc = [](double n) { return n / 2.0 > 48.0 ? n / 2.0 : 48.0; };
         const double m_tiles = L.kind == hmv::LK_FLAT ? ceil(M / 128.0) : static_cast<double>(r.units) * L.tc.p.tpi;
         double mmas = m_tiles * (L.n_alloc / (L.bn > 0 ? L.bn : 1)) * (L.K / 16.0);
+        double mma_cycles = mmas * mma_cyc(L.bn);
         if (r.seam >= 0) {
-            mmas = m_tiles * (8.0 * 16.0 + 64.0);     // 8 conv3 chunks x K 256 + next conv1 K 1024                            // fused conv3(b) + conv1(b+1): conv2 output in, residual in, block output + next conv1 output out
+            mmas = m_tiles * (8.0 * 16.0 + 64.0);     // 8 conv3 chunks x K 256 (N = 128) + next conv1 K 1024 (N = 256)
+            mma_cycles = m_tiles * (8.0 * 16.0 * mma_cyc(128) + 64.0 * mma_cyc(256));
+            // fused conv3(b) + conv1(b+1): conv2 output in, residual in, block output + next conv1 output out
             const hmv::Layer& L1 = h->layers[h->seams[r.seam].l1];
             flop += 2.0 * M * L1.cout * L1.cin;
             bytes += out_bytes(L, M) + res_bytes(L, M) + out_bytes(L1, M) + static_cast<double>(L1.cout) * L1.K * 2.0;
@@ -2289,6 +2294,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
         } else if (r.tail >= 0) {                     // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3 (the conv2 output stays on chip / in L2)
             const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
             mmas = m_tiles * (L.K / 16.0 + (L3.cout / 128.0) * (L3.K / 16.0));
+            mma_cycles = m_tiles * (L.K / 16.0 * mma_cyc(L.cout) + (L3.cout / 128.0) * (L3.K / 16.0) * mma_cyc(128));
             flop += 2.0 * M * L3.cout * L3.cin;
             bytes += out_bytes(L3, M) + res_bytes(L3, M) + static_cast<double>(L3.cout) * L3.K * 2.0;
             name = L.name + "+conv3";
@@ -2297,7 +2303,7 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
             bytes += out_bytes(L, M) + res_bytes(L, M);
         }
         ms += t; fl += flop;
-        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f,%.3f,%.0f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12, bytes * 1e-6, mmas);
+        if (f) fprintf(f, "%s,%.0f,%d,%.0f,%d,%.6f,%.4f,%.2f,%.3f,%.0f,%.0f\n", name.c_str(), M, ncol, kcol, L.bn, t, flop * 1e-9, flop / (t * 1e-3) * 1e-12, bytes * 1e-6, mmas, mma_cycles);
         h->ev_pool.push_back(r.e0); h->ev_pool.push_back(r.e1);
     }
     if (f) fclose(f);
