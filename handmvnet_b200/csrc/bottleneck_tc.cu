@@ -197,7 +197,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     });
                 if (!ok) break;
             }
-            if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 5] = w_empty; p.prof[blockIdx.x * 16 + 6] = w_y2; }
+            if (p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 5] = w_empty; p.prof[blockIdx.x * 24 + 6] = w_y2; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -208,7 +208,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q = 0;                                  // running conv3 chunk counter (TMEM slot = q & 1)
-            long long w_t1e = 0, w_f2 = 0, w_t2e = 0, w_f3 = 0, t_issue = 0;
+            long long w_t1e = 0, w_f2 = 0, w_t2e = 0, w_f3 = 0, t_issue = 0, t_setup = 0, t_mma = 0, t_commit = 0;
             const long long t_start = clock64();
             for (int i = 0; i < n_i + kBtLag; ++i) {
                 const uint32_t a = static_cast<uint32_t>(i) % Cfg::kNA, ause = static_cast<uint32_t>(i) / Cfg::kNA;
@@ -225,11 +225,14 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         if (elect_one()) {
                             const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
                             const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
+                            const long long c1 = p.prof ? clock64() : 0;
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
                                 umma_f16(acc1, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                            const long long c2 = p.prof ? clock64() : 0;
                             umma_commit(empty0 + 8 * stage);
                             if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
+                            if (p.prof) { t_setup += c1 - c0; t_mma += c2 - c1; t_commit += clock64() - c2; }
                         }
                         __syncwarp();
                         if (p.prof) t_issue += clock64() - c0;
@@ -264,8 +267,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 if (!ok) break;
             }
             if (p.prof && lane == 0) {
-                long long* o = p.prof + blockIdx.x * 16;
-                o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i; o[14] = t_issue; o[15] = 0;
+                long long* o = p.prof + blockIdx.x * 24;
+                o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i; o[14] = t_issue; o[15] = 0; o[16] = t_setup; o[17] = t_mma; o[18] = t_commit;
             }
         }
         __syncwarp();
@@ -299,7 +302,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     }
                 }
             }
-            if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 12] = w_ce;
+            if (p.prof && lane == 0) p.prof[blockIdx.x * 24 + 12] = w_ce;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -425,7 +428,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         }
         if (lane == 0 && pending >= 0) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
         if (p.prof && warp == 4 && lane == 0) {
-            long long* o = p.prof + blockIdx.x * 16;
+            long long* o = p.prof + blockIdx.x * 24;
             o[7] = w_t2f; o[8] = w_cf; o[9] = w_t1f; o[10] = w_bulk; o[11] = 0;
         }
         __syncwarp();

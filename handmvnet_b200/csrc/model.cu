@@ -520,20 +520,20 @@ static int run_tail(hmv_handle* h, int tail, int units, cudaStream_t s) {
     if (bt_prof) {                                    // bring-up aid: per-role stall cycles of one launch, printed to stderr
         static long long* dbuf = nullptr;
         static int printed = 0;
-        if (!dbuf) HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 148 * 16 * sizeof(long long)));
-        HMV_CUDA(cudaMemsetAsync(dbuf, 0, 148 * 16 * sizeof(long long), s));
+        if (!dbuf) HMV_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbuf), 148 * 24 * sizeof(long long)));
+        HMV_CUDA(cudaMemsetAsync(dbuf, 0, 148 * 24 * sizeof(long long), s));
         b.p.prof = dbuf;
         const int rc = bt_launch(b, h->num_sms, s);
         if (rc == 0 && units >= 64 && printed < 40) {
-            std::vector<long long> host(148 * 16);
+            std::vector<long long> host(148 * 24);
             HMV_CUDA(cudaStreamSynchronize(s));
             HMV_CUDA(cudaMemcpy(host.data(), dbuf, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            double a[16] = {0};
+            double a[24] = {0};
             const int grid = b.p.num_m_tiles < h->num_sms ? b.p.num_m_tiles : h->num_sms;
-            for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += static_cast<double>(host[c * 16 + k]) / grid;
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) a[k] += static_cast<double>(host[c * 24 + k]) / grid;
             fprintf(stderr, "[bt_prof] %s tiles/cta %.1f total %.0f | mma: t1empty %.0f full2 %.0f t2empty %.0f full3 %.0f | prod: empty %.0f y2ready %.0f | "
-                    "epi: t2full %.0f cfull %.0f t1full %.0f bulk %.0f namedbar %.0f | res: cempty %.0f | mma warp: in the tcgen05.mma + commit issue blocks %.0f (+%.0f) (cycles, mean over CTAs)\n",
-                    T.name.c_str(), a[13], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[14], a[15]);
+                    "epi: t2full %.0f cfull %.0f t1full %.0f bulk %.0f namedbar %.0f | res: cempty %.0f | mma warp: issue blocks %.0f, of which conv2: elect+descriptors %.0f, 4 x tcgen05.mma %.0f, commits %.0f (cycles, mean over CTAs)\n",
+                    T.name.c_str(), a[13], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[14], a[16], a[17], a[18]);
             ++printed;
         }
         return rc;

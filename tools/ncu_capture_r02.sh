@@ -7,14 +7,15 @@ O=gpurun_out/r02; mkdir -p $O
 B="python bench.py --steps 1 --warmup 3 --ramp-seconds 0 --no-e2e --no-eager --no-latency --no-cpu-baseline --no-clocks"
 $B > $O/plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $O/plain_bench.log; exit 1; }
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/ncu_launches_step_dram.csv $B > $O/ncu_step.log 2>&1; echo "ncu launch list rc $?"
-python tools/ncu_step_traffic.py $O/ncu_launches_step_dram.csv gpurun_out/tc_launches.csv $O/tc_traffic.json 5 | tail -22
+# 4 ramp calls + 3 warm-up + 1 timed + 1 per-launch-event pass = 9 identical steps in the capture
+python tools/ncu_step_traffic.py $O/ncu_launches_step_dram.csv gpurun_out/tc_launches.csv $O/tc_traffic.json 9 | tail -22
 cap() {  # name, kernel regex, launches to skip
-  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 1 -f -o $O/$1 $B > $O/$1.log 2>&1; echo "ncu $1 rc $?"
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $O/$1 $B > $O/$1.log 2>&1; echo "ncu $1 rc $?"
 }
 cap seam_l3 bottleneck_next_kernel 16
 cap tail_p64 "bottleneck_tail_kernel<64>" 10
 cap tail_p128 "bottleneck_tail_kernel<128>" 13
-cap conv_l3_conv2 "conv_gemm_tc_kernel<256, 1, 2>" 13
+cap conv_l3_conv2 "conv_gemm_tc_kernel<256, 1, 4>" 13
 cap stem_pool stem_pool_kernel 3
 cap fusion_block fusion_block_kernel 15
 python tools/ncu_summary.py $O $O > $O/ncu_summary.log 2>&1; tail -12 $O/ncu_summary.log
