@@ -91,7 +91,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                        const __grid_constant__ CUtensorMap tmY2l,  // conv2 output [rows, P], load box {64, 128}
                        const __grid_constant__ CUtensorMap tmW3,   // [4P, P] box {64, 128}
                        const __grid_constant__ CUtensorMap tmOut,  // block output [rows, 4P], store box {64, 32}
-                       const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 4P], load box {64, 128}
+                       const __grid_constant__ CUtensorMap tmRes,  // residual [rows, 4P], load box {64, 128} (ds_kb > 0: the block input [rows, 64 * ds_kb])
+                       const __grid_constant__ CUtensorMap tmWd,   // ds_kb > 0: downsample weights [4P, 64 * ds_kb], box {64, 128}
                        const __grid_constant__ BtParams p,
                        const __grid_constant__ BiasBank bank) {            // conv2 biases [0, P), conv3 biases [256, 256 + 4P)
     using Cfg = BtCfg<P>;
@@ -181,14 +182,19 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         // Y2[m3] was TMA-stored by this CTA's epilogue; wait until those stores have completed
                         if (c == 0 && !timed_wait(y2ready0 + 8 * (j3 & 1), static_cast<uint32_t>(j3 >> 1) & 1u, p.err_flag, 22, w_y2, prof)) return false;
                         if (c == 0) fence_proxy_async_all();      // (every lane: the elected one is not known in advance)
-                        for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
+                        for (int kb3 = 0; kb3 < Cfg::kKB3 + p.ds_kb; ++kb3) {     // (+ the folded downsample's K blocks: block input x its weights)
                             if (!timed_wait(empty0 + 8 * stage, phase ^ 1, p.err_flag, 23, w_empty, prof)) return false;
                             if (elect_one()) {
                                 const uint32_t fb = full0 + 8 * stage;
                                 const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                                 mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
-                                tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
-                                tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                                if (kb3 < Cfg::kKB3) {
+                                    tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
+                                    tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                                } else {
+                                    tma_load_2d(sa, &tmRes, fb, (kb3 - Cfg::kKB3) * kTcBlockK, m3 * kTcBlockM);
+                                    tma_load_2d(sa + Cfg::kABytes, &tmWd, fb, (kb3 - Cfg::kKB3) * kTcBlockK, c * kBtN3);
+                                }
                             }
                             __syncwarp();
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -244,7 +250,8 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         if (!timed_wait(t2empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 26, w_t2e, prof)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBtAcc2Col + s * kBtN3;
-                        for (int kb3 = 0; kb3 < Cfg::kKB3; ++kb3) {
+                        const int nk3 = Cfg::kKB3 + p.ds_kb;
+                        for (int kb3 = 0; kb3 < nk3; ++kb3) {
                             if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 27, w_f3, prof)) return false;
                             tc_fence_after();
                             const long long c0 = p.prof ? clock64() : 0;
@@ -255,7 +262,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                 for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
                                     umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb3 | k) != 0 ? 1u : 0u);
                                 umma_commit(empty0 + 8 * stage);
-                                if (kb3 == Cfg::kKB3 - 1) umma_commit(t2full0 + 8 * s);
+                                if (kb3 == nk3 - 1) umma_commit(t2full0 + 8 * s);
                             }
                             __syncwarp();
                             if (p.prof) t_issue += clock64() - c0;
@@ -279,7 +286,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
             bool alive = true;
             long long w_ce = 0;
             for (int i = 0; i < n_i + kBtLag && alive; ++i) {
-                if (p.prefetch && i + 1 >= kBtLag && i + 1 - kBtLag < n_i && lane == 0)      // next segment's residual tile: HBM -> L2 ahead of its slot loads
+                if (p.prefetch && !p.ds_kb && i + 1 >= kBtLag && i + 1 - kBtLag < n_i && lane == 0)      // next segment's residual tile: HBM -> L2 ahead of its slot loads
                     for (int c = 0; c < Cfg::kNCH * 2; ++c) tma_prefetch_l2_2d(&tmRes, c * kBtChunkCols, tile_of(i + 1 - kBtLag) * kTcBlockM);
                 __syncwarp();
                 if (i >= kBtLag) {
@@ -288,8 +295,12 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         const uint32_t slot = g % kBtSlots, use = g / kBtSlots;
                         if (!timed_wait(cempty0 + 8 * slot, (use & 1u) ^ 1u, p.err_flag, 28, w_ce, prof)) { alive = false; break; }
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(cfull0 + 8 * slot, kBtChunkBytes);
-                            tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
+                            if (p.ds_kb) {                  // folded downsample: no residual to fetch, plain hand-over
+                                mbar_arrive(cfull0 + 8 * slot);
+                            } else {
+                                mbar_arrive_expect_tx(cfull0 + 8 * slot, kBtChunkBytes);
+                                tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
+                            }
                         }
                         __syncwarp();
                     }
@@ -392,7 +403,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 #pragma unroll 1
                     for (int cc = 0; cc < kBtN3 / kBtChunkCols && alive; ++cc, ++g) {     // two chunks: one per team
                         if ((g & 1u) != team) continue;
-                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, kBtBias3Off + c * kBtN3 + cc * kBtChunkCols, true, t2empty0 + 8 * s, &tmOut,
+                        do_chunk(kBtAcc2Col + s * kBtN3 + cc * kBtChunkCols, kBtBias3Off + c * kBtN3 + cc * kBtChunkCols, p.ds_kb == 0, t2empty0 + 8 * s, &tmOut,
                                  c * kBtN3 + cc * kBtChunkCols, m3 * kTcBlockM);
                     }
                 }
@@ -446,7 +457,7 @@ template <int P>
 int bt_launch_p(const BtLaunch& l, int num_sms, cudaStream_t stream) {
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
     HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
-                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.p, l.bank));
+                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
     return 0;
 }
 

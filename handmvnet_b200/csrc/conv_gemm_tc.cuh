@@ -78,11 +78,13 @@ struct BtParams {
     int* err_flag;
     long long* prof;                   // optional [grid][16] stall counters (HMV_BT_PROF=1), else null
     int prefetch;                      // 1: L2-prefetch the next tile's residual (HMV_BN_PREFETCH=0 disables)
+    int ds_kb;                         // > 0: the block's 1x1 stride-1 downsample is folded into conv3 as ds_kb extra K blocks per chunk
+                                       //      (A = the block input through `tmRes`, B = `tmWd`); no residual is read then
 };
 constexpr int kBtBias3Off = 256;       // BiasBank layout of the fused tail: conv2 biases at [0, P), conv3 biases at [256, 256 + 4P)
 struct BtLaunch {
     BiasBank bank;
-    CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes;
+    CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes, tmWd;
     BtParams p;
     int planes;                        // P in {64, 128, 256}
 };

@@ -120,6 +120,7 @@ struct Step {
 struct FusedTail {
     std::string name;
     int l2 = -1, l3 = -1;                         // the two layers it covers (weights, biases, maps live there)
+    int l_ds = -1;                                // the block's downsample when it is folded into conv3 (layer1.0)
     BtLaunch bt{};
 };
 
@@ -711,7 +712,7 @@ static int add_gemm_step(hmv_handle* h, const std::string& name, int layer, void
 
 // Fused launch plan for the conv2 (3x3) / conv3 (1x1 + residual) pair of one bottleneck; reuses the tensor maps the
 // two layers already own and adds the reload map of the conv2 output and the chunked conv3 weight map.
-static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
+static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3, int l_ds = -1) {
     const Layer& A = h->layers[l2];
     const Layer& B = h->layers[l3];
     const int P = A.cout;
@@ -737,6 +738,22 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3) {
     memset(&b.bank, 0, sizeof(b.bank));
     memcpy(b.bank.v, A.bias_host.data(), sizeof(float) * P);
     memcpy(b.bank.v + kBtBias3Off, B.bias_host.data(), sizeof(float) * 4 * P);
+    b.tmWd = b.tmW3;                                   // valid placeholder
+    T.l_ds = l_ds;
+    if (l_ds >= 0) {
+        // The block's 1x1 stride-1 downsample (resnet.py:145-146, `identity = self.downsample(x)`) folded into conv3: its K
+        // blocks (block input x folded weights) accumulate into the same TMEM accumulator, the biases add up, and neither the
+        // downsample launch nor the write + re-read of its 4P-channel output exist any more.
+        const Layer& D = h->layers[l_ds];
+        HMV_CHECK(D.kind == LK_FLAT && D.cout == 4 * P && D.K % 64 == 0 && D.K == D.cin && D.max_units * D.rows_per_unit() == static_cast<int64_t>(rows),
+                  "fused bottleneck tail: the folded downsample must be a 1x1 stride-1 conv over the tile's rows in " + name);
+        b.p.ds_kb = D.K / 64;
+        if (tc_make_tmap_out(&b.tmRes, D.in, D.K, rows, 128) || tc_make_tmap_out(&b.tmWd, D.w, D.K, 4 * P, 128)) {
+            set_error(std::string(get_error()) + " [fused-tail downsample maps of " + name + "]");
+            return 1;
+        }
+        for (int j = 0; j < 4 * P; ++j) b.bank.v[kBtBias3Off + j] += D.bias_host[j];
+    }
     b.p.err_flag = h->err_flag_dev;
     {
         const char* e = getenv("HMV_BN_PREFETCH");         // measured neutral (P = 64) to harmful (P = 128): off
@@ -871,15 +888,21 @@ static int build_backbone(hmv_handle* h) {
             if (!fuse) add_gemm_step(h, sp + ".conv2", idx2, h->bufT2, pl, H / st, W / st, {{h->bufT1, sp + ".conv1", pl, H, W}});
             const void* res = cur;
             StepIO res_io{cur, cur_name, C, H, W};
+            int idx_ds = -1;
             if (ds) {
                 if (add_conv(h, sp + ".downsample", p + ".downsample.0", p + ".downsample.1", false, C, pl * 4, 1, st, H, W, cur, h->bufDS, ACT_NONE, nullptr, &idx)) return 1;
-                add_gemm_step(h, sp + ".downsample", idx, h->bufDS, pl * 4, H / st, W / st, {{cur, cur_name, C, H, W}});
+                static const bool fold_ds = [] { const char* e = getenv("HMV_FOLD_DS"); return !(e && e[0] == '0'); }();
+                if (fuse && fold_ds && st == 1 && C % 64 == 0) {
+                    idx_ds = idx;                            // folded into the fused tail below: no launch, no step of its own
+                } else {
+                    add_gemm_step(h, sp + ".downsample", idx, h->bufDS, pl * 4, H / st, W / st, {{cur, cur_name, C, H, W}});
+                    res_io = StepIO{h->bufDS, sp + ".downsample", pl * 4, H / st, W / st};
+                }
                 res = h->bufDS;
-                res_io = StepIO{h->bufDS, sp + ".downsample", pl * 4, H / st, W / st};
             }
             if (add_conv(h, sp + ".conv3", p + ".conv3", p + ".bn3", false, pl, pl * 4, 1, 1, H / st, W / st, h->bufT2, nxt, ACT_RELU, res, &idx)) return 1;
             if (fuse) {
-                if (add_tail(h, sp + ".conv3", idx2, idx)) return 1;
+                if (add_tail(h, sp + ".conv3", idx2, idx, idx_ds)) return 1;
                 Step ts; ts.kind = SK_TAIL; ts.name = sp + ".conv3"; ts.layer = static_cast<int>(h->tails.size()) - 1;
                 ts.out = nxt; ts.C = pl * 4; ts.H = H / st; ts.W = W / st;
                 ts.ins.push_back({h->bufT1, sp + ".conv1", pl, H, W});
@@ -2293,12 +2316,14 @@ int hmv_profile_read(hmv_handle* h, double* tc_ms, double* tc_flops, int64_t* tc
             name = L.name + "+next.conv1";
         } else if (r.tail >= 0) {                     // fused conv2 + conv3: both GEMMs' work, N / K columns of conv3 (the conv2 output stays on chip / in L2)
             const hmv::Layer& L3 = h->layers[h->tails[r.tail].l3];
-            mmas = m_tiles * (L.K / 16.0 + (L3.cout / 128.0) * (L3.K / 16.0));
-            mma_cycles = m_tiles * (L.K / 16.0 * mma_cyc(L.cout) + (L3.cout / 128.0) * (L3.K / 16.0) * mma_cyc(128));
-            flop += 2.0 * M * L3.cout * L3.cin;
-            bytes += out_bytes(L3, M) + res_bytes(L3, M) + static_cast<double>(L3.cout) * L3.K * 2.0;
-            name = L.name + "+conv3";
-            ncol = L3.cout; kcol = kreal + L3.cin;
+            const int l_ds = h->tails[r.tail].l_ds;
+            const double k_ds = l_ds >= 0 ? h->layers[l_ds].K : 0.0;          // folded downsample: extra K of conv3, block input instead of a residual
+            mmas = m_tiles * (L.K / 16.0 + (L3.cout / 128.0) * ((L3.K + k_ds) / 16.0));
+            mma_cycles = m_tiles * (L.K / 16.0 * mma_cyc(L.cout) + (L3.cout / 128.0) * ((L3.K + k_ds) / 16.0) * mma_cyc(128));
+            flop += 2.0 * M * L3.cout * (L3.cin + k_ds);
+            bytes += out_bytes(L3, M) + static_cast<double>(L3.cout) * (L3.K + k_ds) * 2.0 + (l_ds >= 0 ? M * k_ds * 2.0 : res_bytes(L3, M));
+            name = L.name + (l_ds >= 0 ? "+conv3+downsample" : "+conv3");
+            ncol = L3.cout; kcol = kreal + L3.cin + k_ds;
         } else {
             bytes += out_bytes(L, M) + res_bytes(L, M);
         }
