@@ -83,7 +83,7 @@ __device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* e
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int P>
+template <int P, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 input, 5-D activation map
                        const __grid_constant__ CUtensorMap tmW2,   // [P, 9P] box {64, P}
@@ -150,7 +150,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 
     const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
-    const bool prof = p.prof != nullptr;
+    constexpr bool prof = PROF;                               // stall counters compiled in only for HMV_BT_PROF=1 launches
 
     if (warp == 0) {
         // ===================== TMA producer of the operand ring =====================
@@ -203,7 +203,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     });
                 if (!ok) break;
             }
-            if (p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 5] = w_empty; p.prof[blockIdx.x * 24 + 6] = w_y2; }
+            if (PROF && p.prof && lane == 0) { p.prof[blockIdx.x * 24 + 5] = w_empty; p.prof[blockIdx.x * 24 + 6] = w_y2; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -227,21 +227,21 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         }
                         if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 25, w_f2, prof)) return false;
                         tc_fence_after();
-                        const long long c0 = p.prof ? clock64() : 0;
+                        const long long c0 = PROF ? clock64() : 0;
                         if (elect_one()) {
                             const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
                             const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
-                            const long long c1 = p.prof ? clock64() : 0;
+                            const long long c1 = PROF ? clock64() : 0;
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
                                 umma_f16(acc1, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
-                            const long long c2 = p.prof ? clock64() : 0;
+                            const long long c2 = PROF ? clock64() : 0;
                             umma_commit(empty0 + 8 * stage);
                             if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
-                            if (p.prof) { t_setup += c1 - c0; t_mma += c2 - c1; t_commit += clock64() - c2; }
+                            if (PROF) { t_setup += c1 - c0; t_mma += c2 - c1; t_commit += clock64() - c2; }
                         }
                         __syncwarp();
-                        if (p.prof) t_issue += clock64() - c0;
+                        if (PROF) t_issue += clock64() - c0;
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         return true;
                     },
@@ -254,7 +254,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                         for (int kb3 = 0; kb3 < nk3; ++kb3) {
                             if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 27, w_f3, prof)) return false;
                             tc_fence_after();
-                            const long long c0 = p.prof ? clock64() : 0;
+                            const long long c0 = PROF ? clock64() : 0;
                             if (elect_one()) {
                                 const uint64_t adesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes);
                                 const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
@@ -265,7 +265,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                 if (kb3 == nk3 - 1) umma_commit(t2full0 + 8 * s);
                             }
                             __syncwarp();
-                            if (p.prof) t_issue += clock64() - c0;
+                            if (PROF) t_issue += clock64() - c0;
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         }
                         ++q;
@@ -273,7 +273,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     });
                 if (!ok) break;
             }
-            if (p.prof && lane == 0) {
+            if (PROF && p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 24;
                 o[0] = clock64() - t_start; o[1] = w_t1e; o[2] = w_f2; o[3] = w_t2e; o[4] = w_f3; o[13] = n_i; o[14] = t_issue; o[15] = 0; o[16] = t_setup; o[17] = t_mma; o[18] = t_commit;
             }
@@ -313,7 +313,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     }
                 }
             }
-            if (p.prof && lane == 0) p.prof[blockIdx.x * 24 + 12] = w_ce;
+            if (PROF && p.prof && lane == 0) p.prof[blockIdx.x * 24 + 12] = w_ce;
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -383,9 +383,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         // now, and the slot goes back to the residual prefetcher ahead of its next use.
         auto release_pending = [&]() {
             if (lane == 0 && pending >= 0) {
-                const long long tb = clock64();
-                bulk_wait_read<0>();
-                w_bulk += clock64() - tb;
+                if (PROF) { const long long tb = clock64(); bulk_wait_read<0>(); w_bulk += clock64() - tb; } else bulk_wait_read<0>();
                 mbar_arrive(cempty0 + 8 * pending);
                 pending = -1;
             }
@@ -427,9 +425,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                              cc * kBtChunkCols, m2 * kTcBlockM);
                 }
                 if (mine && lane == 0) {                     // Y2[m2] must be complete in global memory before it is reloaded
-                    const long long tb = clock64();
-                    bulk_wait_all();
-                    w_bulk += clock64() - tb;
+                    if (PROF) { const long long tb = clock64(); bulk_wait_all(); w_bulk += clock64() - tb; } else bulk_wait_all();
                     if (pending >= 0) mbar_arrive(cempty0 + 8 * pending);
                     pending = -1;
                     fence_proxy_async_all();
@@ -438,7 +434,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
             }
         }
         if (lane == 0 && pending >= 0) bulk_wait_read<0>();  // staged data must stay valid until every store has read it
-        if (p.prof && warp == 4 && lane == 0) {
+        if (PROF && p.prof && warp == 4 && lane == 0) {
             long long* o = p.prof + blockIdx.x * 24;
             o[7] = w_t2f; o[8] = w_cf; o[9] = w_t1f; o[10] = w_bulk; o[11] = 0;
         }
@@ -456,17 +452,24 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 template <int P>
 int bt_launch_p(const BtLaunch& l, int num_sms, cudaStream_t stream) {
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
-    HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
-                           l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
+    if (l.p.prof)
+        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, true>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
+                               l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
+    else
+        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, false>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
+                               l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
     return 0;
 }
 
 }  // namespace
 
 int bt_init() {
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
     return 0;
 }
 
