@@ -13,9 +13,9 @@ cap() {  # name, kernel regex, launches to skip
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $O/$1 $B > $O/$1.log 2>&1; echo "ncu $1 rc $?"
 }
 cap seam_l3 bottleneck_next_kernel 16
-cap tail_p64 "bottleneck_tail_kernel<64>" 10
-cap tail_p128 "bottleneck_tail_kernel<128>" 13
-cap conv_l3_conv2 "conv_gemm_tc_kernel<256, 1, 4>" 13
+cap tail_p64 "bottleneck_tail_kernel<\(int\)64" 10
+cap tail_p128 "bottleneck_tail_kernel<\(int\)128" 13
+cap conv_l3_conv2 "conv_gemm_tc_kernel<\(int\)256, \(int\)1, \(int\)4>" 13
 cap stem_pool stem_pool_kernel 3
 cap fusion_block fusion_block_kernel 15
 python tools/ncu_summary.py $O $O > $O/ncu_summary.log 2>&1; tail -12 $O/ncu_summary.log
@@ -26,8 +26,8 @@ python - <<'PY'
 import csv, collections
 rows = [ln for ln in open("gpurun_out/r02/ncu_launches_b1.csv") if ln.startswith('"')]
 ks = [r for r in csv.DictReader(rows) if r["Metric Name"] == "gpu__time_duration.sum" and "hmv::" in r["Kernel Name"]]
-# the first model is 5 views B=1: 70 forwards x 49 kernels; take the last forward of that model
-per = 49
+# the first model is 5 views B=1: 70 forwards x 48 kernels; take the last forward of that model
+per = 48
 first = ks[: 70 * per][-per:]
 tot = 0.0
 agg = collections.OrderedDict()
