@@ -224,7 +224,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                         for (int kb = 0; kb < kBnKb3; ++kb) tma_load_2d(y2_base + kb * 16384, &tmY2, y2full, kb * kTcBlockK, m * kTcBlockM);
                     }
                 }
-                __syncwarp();
                 const bool ok = bn_tile_schedule<BnGeo<PAIR>::kLag>(
                     [&](int c) {
                         for (int s2 = 0; s2 < kBnKb3 / 2; ++s2) {          // a stage = two K blocks of this chunk's weights
@@ -244,7 +243,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                                     for (int hb = 0; hb < 2; ++hb) tma_load_2d(sb + hb * kBnHalfBytes, &tmW3, fb, (2 * s2 + hb) * kTcBlockK, c * kBnChunk);
                                 }
                             }
-                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -263,7 +261,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                                     tma_load_2d(smem_base + stage * kBnStageBytes, &tmW1, fb, (2 * c + j) * kTcBlockK, 0);
                                 }
                             }
-                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -326,7 +323,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                                     if (c == kBnNch - 1) commit(y2empty);                  // the tile's Y2 is no longer needed (both CTAs of a pair)
                                 }
                             }
-                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         ++q3;
@@ -351,7 +347,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                                 commit(sfree0 + 8 * slot);                                 // the slot's MMAs have retired (in both CTAs of a pair)
                                 if (c == kBnNch - 1 && j == 1) commit(t1full);
                             }
-                            __syncwarp();
                             if (++stage == kBnStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -384,7 +379,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             mbar_arrive(sfree0 + 8 * slot);  // stands in for the MMA commit: conv1 slots feed no MMA
                         }
                     }
-                    __syncwarp();
                 }
             }
             if (PROF && p.prof && lane == 0) p.prof[blockIdx.x * 24 + 8] = w_sf;
@@ -414,7 +408,6 @@ bottleneck_next_kernel(const __grid_constant__ CUtensorMap tmY2,   // conv2 outp
                             mbar_arrive(sfree0 + 8 * ((g - HMV_BN_STORE_DEPTH) % kBnSlots));
                         }
                     }
-                    __syncwarp();
                 }
             }
             if (elect_one()) bulk_wait_read<0>();            // staged data must stay valid until every store has read it

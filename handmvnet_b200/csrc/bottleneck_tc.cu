@@ -174,7 +174,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                             tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
                             tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
                         }
-                        __syncwarp();
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         return true;
                     },
@@ -196,7 +195,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                     tma_load_2d(sa + Cfg::kABytes, &tmWd, fb, (kb3 - Cfg::kKB3) * kTcBlockK, c * kBtN3);
                                 }
                             }
-                            __syncwarp();
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         }
                         return true;
@@ -240,7 +238,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                             if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
                             if (PROF) { t_setup += c1 - c0; t_mma += c2 - c1; t_commit += clock64() - c2; }
                         }
-                        __syncwarp();
                         if (PROF) t_issue += clock64() - c0;
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         return true;
@@ -264,7 +261,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                 umma_commit(empty0 + 8 * stage);
                                 if (kb3 == nk3 - 1) umma_commit(t2full0 + 8 * s);
                             }
-                            __syncwarp();
                             if (PROF) t_issue += clock64() - c0;
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         }
@@ -302,7 +298,6 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                 tma_load_2d(slots_base + slot * kBtChunkBytes, &tmRes, cfull0 + 8 * slot, c * kBtChunkCols, m3 * kTcBlockM);
                             }
                         }
-                        __syncwarp();
                     }
                 }
                 if (i < n_i) {

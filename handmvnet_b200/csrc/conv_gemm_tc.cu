@@ -214,7 +214,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     tma_load_2d(sa + Cfg::kABytes, &tmB, fb, kb * kTcBlockK, n_tile * BN);
                             }
                         }
-                        __syncwarp();
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -255,7 +254,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             else umma_commit(tfull0 + 8 * acc);      // accumulator ready for the epilogue
                         }
                     }
-                    __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (!alive) break;
@@ -281,7 +279,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_load_2d(rbuf0 + slot * kChunkBytes, &tmR, cfull0 + 8 * slot, n_tile * BN + c * kChunkCols,
                                     m_tile * p.tile_rows);
                     }
-                    __syncwarp();
                 }
             }
         }

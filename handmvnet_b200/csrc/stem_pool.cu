@@ -195,7 +195,6 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
                             for (int q = 1; q < 4; ++q) umma_commit(pempty0 + 8 * ((gq + t + q) % kRingSlots));
                         umma_commit(afull0 + 8 * acc);
                     }
-                    __syncwarp();
                 }
                 gq += nrows + 3;
             }
