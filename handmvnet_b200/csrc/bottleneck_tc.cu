@@ -18,6 +18,7 @@
 // Shared memory: kStages operand stages (A 16 KiB + B max(P*128, 16 KiB)) and ONE ring of 4 chunk slots
 // (128 rows x 64 bf16, 128B swizzle) that serves both as residual landing zone (TMA load by warp 2) and as store
 // staging (the epilogue adds bias/residual in place, then TMA-stores the slot).
+#include <map>
 #include "conv_gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -32,11 +33,12 @@ constexpr int kBtAcc2Col = 256;                                 // TMEM column o
 constexpr int kBtN3 = 128;                                      // conv3 chunk width
 constexpr int kBtLag = 2;                                       // conv3 of tile i-kBtLag runs inside the K loop of tile i
 
-template <int P>
+template <int P, bool PAIR = false>
 struct BtCfg {
     static constexpr int kABytes = kTcBlockM * kTcBlockK * 2;                  // 16 KiB
-    static constexpr int kB2Bytes = P * kTcBlockK * 2;
-    static constexpr int kB3Bytes = kBtN3 * kTcBlockK * 2;                     // 16 KiB
+    // CTA pair (cta_group::2): a CTA holds its own A rows and HALF of every weight tile
+    static constexpr int kB2Bytes = (PAIR ? P / 2 : P) * kTcBlockK * 2;
+    static constexpr int kB3Bytes = (PAIR ? kBtN3 / 2 : kBtN3) * kTcBlockK * 2;
     static constexpr int kBSlot = kB2Bytes > kB3Bytes ? kB2Bytes : kB3Bytes;
     static constexpr int kStageBytes = kABytes + kBSlot;
     static constexpr int kStagesRaw = (226 * 1024 - kBtSlots * kBtChunkBytes - 1024) / kStageBytes;
@@ -83,7 +85,11 @@ __device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* e
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int P, bool PROF>
+// PAIR: launched as clusters of two CTAs on neighbouring M tiles; the leader (rank 0) issues tcgen05.mma.cta_group::2 of M = 256 for
+// both (A rows from both CTAs' shared memory at the same offsets, half of each weight tile from each).  Both CTAs' TMA loads
+// count on the leader's `full` barriers, the leader's commits arrive on `empty` / `t1full` / `t2full` in both CTAs, and the peer's
+// epilogue warps arrive on the leader's `t1empty` / `t2empty` remotely.  The weights cross L2 -> SM once per pair.
+template <int P, bool PROF, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 input, 5-D activation map
                        const __grid_constant__ CUtensorMap tmW2,   // [P, 9P] box {64, P}
@@ -95,7 +101,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                        const __grid_constant__ CUtensorMap tmWd,   // ds_kb > 0: downsample weights [4P, 64 * ds_kb], box {64, 128}
                        const __grid_constant__ BtParams p,
                        const __grid_constant__ BiasBank bank) {            // conv2 biases [0, P), conv3 biases [256, 256 + 4P)
-    using Cfg = BtCfg<P>;
+    using Cfg = BtCfg<P, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* slots = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -115,6 +121,13 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    constexpr uint32_t kCtas = PAIR ? 2u : 1u;
+    // arrive on a barrier the MMA issuer waits on: in a pair that barrier lives in the leader CTA
+    auto arrive_mma = [&](uint32_t bar) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(bar, 0));
+        else mbar_arrive(bar);
+    };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmW2); prefetch_tmap(&tmY2s); prefetch_tmap(&tmY2l);
@@ -125,9 +138,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(t1full0 + 8 * i, 1);
-            mbar_init(t1empty0 + 8 * i, P == 64 ? 4 : 8);   // one arrival per epilogue warp that reads the conv2 accumulator (P = 64: one chunk, one team)
+            mbar_init(t1empty0 + 8 * i, (P == 64 ? 4 : 8) * kCtas);   // one arrival per epilogue warp that reads the conv2 accumulator (P = 64: one chunk, one team), of both CTAs of a pair
             mbar_init(t2full0 + 8 * i, 1);
-            mbar_init(t2empty0 + 8 * i, 8);
+            mbar_init(t2empty0 + 8 * i, 8 * kCtas);
             mbar_init(y2ready0 + 8 * i, P == 64 ? 4 : 8);   // every warp that stored a slab of Y2[m]
         }
         for (int i = 0; i < kBtSlots; ++i) {
@@ -137,19 +150,31 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything remote lands on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     pdl_wait();
     pdl_launch_dependents();
 
-    const int n_i = (p.num_m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+    // one CTA per tile: this CTA's tiles are blockIdx.x, + gridDim.x, ...   pair: the cluster walks pairs of M tiles (the tile
+    // count is even) and this CTA takes tile 2 * pair + rank
+    const int units = PAIR ? p.num_m_tiles / 2 : p.num_m_tiles;
+    const int first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int n_i = (units - first + step - 1) / step;
+    auto tile_of = [&](int i) { return PAIR ? 2 * (first + i * step) + static_cast<int>(crank) : first + i * step; };
     constexpr bool prof = PROF;                               // stall counters compiled in only for HMV_BT_PROF=1 launches
 
     if (warp == 0) {
@@ -170,9 +195,16 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                             const int cb = kb % (P / kTcBlockK);
                             const uint32_t fb = full0 + 8 * stage;
                             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                            mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB2Bytes);
-                            tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
-                            tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
+                            if (PAIR) {        // own A rows + this CTA's half of the weight rows; both CTAs' bytes are counted on the LEADER's barrier
+                                const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (Cfg::kABytes + Cfg::kB2Bytes));
+                                tma_load_5d_2sm(sa, &tmA, lfb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
+                                tma_load_2d_2sm(sa + Cfg::kABytes, &tmW2, lfb, kb * kTcBlockK, static_cast<int>(crank) * (P / 2));
+                            } else {
+                                mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB2Bytes);
+                                tma_load_5d(sa, &tmA, fb, tap.c_off + cb * kTcBlockK, tap.dw, tap.a, h0 + tap.dh, img);
+                                tma_load_2d(sa + Cfg::kABytes, &tmW2, fb, kb * kTcBlockK, 0);
+                            }
                         }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         return true;
@@ -186,13 +218,18 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                             if (elect_one()) {
                                 const uint32_t fb = full0 + 8 * stage;
                                 const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                                mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
-                                if (kb3 < Cfg::kKB3) {
-                                    tma_load_2d(sa, &tmY2l, fb, kb3 * kTcBlockK, m3 * kTcBlockM);
-                                    tma_load_2d(sa + Cfg::kABytes, &tmW3, fb, kb3 * kTcBlockK, c * kBtN3);
+                                const CUtensorMap* ma = kb3 < Cfg::kKB3 ? &tmY2l : &tmRes;      // conv2 output / (folded downsample) block input
+                                const CUtensorMap* mb = kb3 < Cfg::kKB3 ? &tmW3 : &tmWd;
+                                const int kc = (kb3 < Cfg::kKB3 ? kb3 : kb3 - Cfg::kKB3) * kTcBlockK;
+                                if (PAIR) {
+                                    const uint32_t lfb = crank == 0 ? fb : mapa_u32(fb, 0);
+                                    if (crank == 0) mbar_arrive_expect_tx(fb, 2u * (Cfg::kABytes + Cfg::kB3Bytes));
+                                    tma_load_2d_2sm(sa, ma, lfb, kc, m3 * kTcBlockM);
+                                    tma_load_2d_2sm(sa + Cfg::kABytes, mb, lfb, kc, c * kBtN3 + static_cast<int>(crank) * (kBtN3 / 2));
                                 } else {
-                                    tma_load_2d(sa, &tmRes, fb, (kb3 - Cfg::kKB3) * kTcBlockK, m3 * kTcBlockM);
-                                    tma_load_2d(sa + Cfg::kABytes, &tmWd, fb, (kb3 - Cfg::kKB3) * kTcBlockK, c * kBtN3);
+                                    mbar_arrive_expect_tx(fb, Cfg::kABytes + Cfg::kB3Bytes);
+                                    tma_load_2d(sa, ma, fb, kc, m3 * kTcBlockM);
+                                    tma_load_2d(sa + Cfg::kABytes, mb, fb, kc, c * kBtN3);
                                 }
                             }
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -206,9 +243,25 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        {   // the whole warp walks the schedule and waits; one elected lane issues (see elect_one() in tc_ptx.cuh for why)
-            constexpr uint32_t idesc2 = make_idesc(P);
-            constexpr uint32_t idesc3 = make_idesc(kBtN3);
+        if (crank == 0) {                                    // pair: only the leader issues, for both CTAs
+            // the whole warp walks the schedule and waits; one elected lane issues (see elect_one() in tc_ptx.cuh for why)
+            constexpr uint32_t idesc2 = PAIR ? make_idesc_mn(2 * kTcBlockM, P) : make_idesc(P);
+            constexpr uint32_t idesc3 = PAIR ? make_idesc_mn(2 * kTcBlockM, kBtN3) : make_idesc(kBtN3);
+            auto wait_epi = [&](uint32_t bar, uint32_t parity, int code, long long& acc) {      // barriers the epilogue warps arrive on
+                if (!PAIR) return timed_wait(bar, parity, p.err_flag, code, acc, prof);
+                const long long t0 = PROF ? clock64() : 0;
+                const bool ok = mbar_wait_cluster(bar, parity, p.err_flag, code);
+                if (PROF) acc += clock64() - t0;
+                return ok;
+            };
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+                if (PAIR) umma_f16_2sm(d, a, b, idesc, accum);
+                else umma_f16(d, a, b, idesc, accum);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) umma_commit_2sm_mc(bar, static_cast<uint16_t>(3));
+                else umma_commit(bar);
+            };
             int stage = 0;
             uint32_t phase = 0;
             uint32_t q = 0;                                  // running conv3 chunk counter (TMEM slot = q & 1)
@@ -220,7 +273,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 const bool ok = bt_segment<P>(i < n_i, i >= kBtLag,
                     [&](int kb) {
                         if (kb == 0) {                       // this conv2 accumulator was drained by the epilogue of its previous tile
-                            if (!timed_wait(t1empty0 + 8 * a, (ause & 1u) ^ 1u, p.err_flag, 24, w_t1e, prof)) return false;
+                            if (!wait_epi(t1empty0 + 8 * a, (ause & 1u) ^ 1u, 24, w_t1e)) return false;
                             tc_fence_after();
                         }
                         if (!timed_wait(full0 + 8 * stage, phase, p.err_flag, 25, w_f2, prof)) return false;
@@ -232,10 +285,10 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                             const long long c1 = PROF ? clock64() : 0;
 #pragma unroll
                             for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)       // +32 bytes of K per MMA = +2 in the address field
-                                umma_f16(acc1, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                                mma(acc1, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
                             const long long c2 = PROF ? clock64() : 0;
-                            umma_commit(empty0 + 8 * stage);
-                            if (kb == Cfg::kKB2 - 1) umma_commit(t1full0 + 8 * a);
+                            commit(empty0 + 8 * stage);
+                            if (kb == Cfg::kKB2 - 1) commit(t1full0 + 8 * a);
                             if (PROF) { t_setup += c1 - c0; t_mma += c2 - c1; t_commit += clock64() - c2; }
                         }
                         if (PROF) t_issue += clock64() - c0;
@@ -244,7 +297,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                     },
                     [&](int) {
                         const uint32_t s = q & 1u, use = q >> 1;
-                        if (!timed_wait(t2empty0 + 8 * s, (use & 1u) ^ 1u, p.err_flag, 26, w_t2e, prof)) return false;
+                        if (!wait_epi(t2empty0 + 8 * s, (use & 1u) ^ 1u, 26, w_t2e)) return false;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + kBtAcc2Col + s * kBtN3;
                         const int nk3 = Cfg::kKB3 + p.ds_kb;
@@ -257,9 +310,9 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                                 const uint64_t bdesc = make_sw128_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes);
 #pragma unroll
                                 for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k)
-                                    umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb3 | k) != 0 ? 1u : 0u);
-                                umma_commit(empty0 + 8 * stage);
-                                if (kb3 == nk3 - 1) umma_commit(t2full0 + 8 * s);
+                                    mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc3, (kb3 | k) != 0 ? 1u : 0u);
+                                commit(empty0 + 8 * stage);
+                                if (kb3 == nk3 - 1) commit(t2full0 + 8 * s);
                             }
                             if (PROF) t_issue += clock64() - c0;
                             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -347,7 +400,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                 if (hf == 1 && release_bar != 0) {           // this warp's part of the accumulator is read: hand TMEM back early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(release_bar);
+                    if (lane == 0) arrive_mma(release_bar);        // (the leader's barrier in a pair)
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -438,42 +491,77 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer may still arrive on this CTA's barriers / the leader's MMAs read this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-template <int P>
+template <int P, bool PAIR>
 int bt_launch_p(const BtLaunch& l, int num_sms, cudaStream_t stream) {
+    using Cfg = BtCfg<P, PAIR>;
+    if (PAIR) {                        // CTA pairs (tmW2 / tmW3 / tmWd carry half-height boxes)
+        HMV_CHECK(l.p.num_m_tiles % 2 == 0, "tail kernel pairs need an even tile count");
+        static std::map<std::pair<int, int>, int> cache;                   // per (device, persistent-grid cap)
+        int dev = 0;
+        HMV_CUDA(cudaGetDevice(&dev));
+        int& max_clusters = cache.emplace(std::make_pair(dev, num_sms), -1).first->second;
+        if (max_clusters < 0) {        // the persistent grid must be co-resident; clusters are placed inside one GPC
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = dim3(2 * (num_sms / 2)); qc.blockDim = dim3(kTcThreads); qc.dynamicSmemBytes = Cfg::kSmemBytes;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int n = 0;
+            HMV_CUDA(cudaOccupancyMaxActiveClusters(&n, bottleneck_tail_kernel<P, false, PAIR>, &qc));
+            HMV_CHECK(n > 0, "no CTA pair of the tail kernel fits on this device");
+            max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+        }
+        const int pairs = l.p.num_m_tiles / 2;
+        const int clusters = pairs < max_clusters ? pairs : max_clusters;
+        if (l.p.prof)
+            HMV_CUDA(launch_kernel_cluster(bottleneck_tail_kernel<P, true, PAIR>, dim3(2 * clusters), dim3(kTcThreads), 2, Cfg::kSmemBytes, stream, l.tmA,
+                                           l.tmW2, l.tmY2s, l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
+        else
+            HMV_CUDA(launch_kernel_cluster(bottleneck_tail_kernel<P, false, PAIR>, dim3(2 * clusters), dim3(kTcThreads), 2, Cfg::kSmemBytes, stream, l.tmA,
+                                           l.tmW2, l.tmY2s, l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
+        return 0;
+    }
     const int grid = l.p.num_m_tiles < num_sms ? l.p.num_m_tiles : num_sms;
     if (l.p.prof)
-        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, true>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
+        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, true, PAIR>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
                                l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
     else
-        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, false>, dim3(grid), dim3(kTcThreads), BtCfg<P>::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
+        HMV_CUDA(launch_kernel(bottleneck_tail_kernel<P, false, PAIR>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, l.tmA, l.tmW2, l.tmY2s,
                                l.tmY2l, l.tmW3, l.tmOut, l.tmRes, l.tmWd, l.p, l.bank));
+    return 0;
+}
+
+template <int P, bool PROF, bool PAIR>
+int bt_attr() {
+    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<P, PROF, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<P, PAIR>::kSmemBytes));
     return 0;
 }
 
 }  // namespace
 
 int bt_init() {
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<64>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<128>::kSmemBytes));
-    HMV_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BtCfg<256>::kSmemBytes));
+    if (bt_attr<64, false, false>() || bt_attr<128, false, false>() || bt_attr<256, false, false>() || bt_attr<64, true, false>() ||
+        bt_attr<128, true, false>() || bt_attr<256, true, false>())
+        return 1;
+    if (bt_attr<64, false, true>() || bt_attr<128, false, true>() || bt_attr<64, true, true>() || bt_attr<128, true, true>()) return 1;
     return 0;
 }
 
 int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.p.num_m_tiles <= 0) return 0;
     switch (l.planes) {
-        case 64: return bt_launch_p<64>(l, num_sms, stream);
-        case 128: return bt_launch_p<128>(l, num_sms, stream);
-        case 256: return bt_launch_p<256>(l, num_sms, stream);
+        case 64: return l.pair ? bt_launch_p<64, true>(l, num_sms, stream) : bt_launch_p<64, false>(l, num_sms, stream);
+        case 128: return l.pair ? bt_launch_p<128, true>(l, num_sms, stream) : bt_launch_p<128, false>(l, num_sms, stream);
+        case 256: return bt_launch_p<256, false>(l, num_sms, stream);
     }
     set_error("bt_launch: unsupported bottleneck width " + std::to_string(l.planes));
     return 1;

@@ -87,6 +87,7 @@ struct BtLaunch {
     CUtensorMap tmA, tmW2, tmY2s, tmY2l, tmW3, tmOut, tmRes, tmWd;
     BtParams p;
     int planes;                        // P in {64, 128, 256}
+    int pair;                          // 1: CTA pairs issuing cta_group::2 MMAs (tmW2 / tmW3 / tmWd carry half-height boxes)
 };
 int bt_init();                                               // shared-memory attributes of the three instantiations
 int bt_launch(const BtLaunch& l, int num_sms, cudaStream_t stream);

@@ -724,11 +724,15 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3, int 
     BtLaunch& b = T.bt;
     memset(&b.p, 0, sizeof(b.p));
     b.planes = P;
-    b.tmA = A.tc.tmA; b.tmY2s = A.tc.tmC;
-    if (tc_make_tmap_wgt(&b.tmW2, A.w, A.K, A.n_alloc, P)) return 1;        // full-height box (the layer's own map may be a half box)
-    b.tmOut = B.tc.tmC; b.tmRes = B.tc.tmR;
     const uint64_t rows = static_cast<uint64_t>(A.max_units) * A.rows_per_unit();
-    if (tc_make_tmap_out(&b.tmY2l, A.ep.out, P, rows, 128) || tc_make_tmap_out(&b.tmW3, B.w, P, 4 * P, 128)) {
+    // CTA-pair variant (cta_group::2, each CTA holds half of every weight tile): large passes of the P = 64 / 128 tails
+    static const bool tail_pair_env = [] { const char* e = getenv("HMV_TAIL_PAIR"); return !(e && e[0] == '0'); }();
+    const bool pair = tail_pair_env && P <= 128 && rows >= 65536 && (rows / 128) % 2 == 0;
+    b.pair = pair ? 1 : 0;
+    b.tmA = A.tc.tmA; b.tmY2s = A.tc.tmC;
+    if (tc_make_tmap_wgt(&b.tmW2, A.w, A.K, A.n_alloc, pair ? P / 2 : P)) return 1;        // (the layer's own map may be a half box)
+    b.tmOut = B.tc.tmC; b.tmRes = B.tc.tmR;
+    if (tc_make_tmap_out(&b.tmY2l, A.ep.out, P, rows, 128) || tc_make_tmap_out(&b.tmW3, B.w, P, 4 * P, pair ? 64 : 128)) {
         set_error(std::string(get_error()) + " [fused-tail maps of " + name + "]");
         return 1;
     }
@@ -748,7 +752,7 @@ static int add_tail(hmv_handle* h, const std::string& name, int l2, int l3, int 
         HMV_CHECK(D.kind == LK_FLAT && D.cout == 4 * P && D.K % 64 == 0 && D.K == D.cin && D.max_units * D.rows_per_unit() == static_cast<int64_t>(rows),
                   "fused bottleneck tail: the folded downsample must be a 1x1 stride-1 conv over the tile's rows in " + name);
         b.p.ds_kb = D.K / 64;
-        if (tc_make_tmap_out(&b.tmRes, D.in, D.K, rows, 128) || tc_make_tmap_out(&b.tmWd, D.w, D.K, 4 * P, 128)) {
+        if (tc_make_tmap_out(&b.tmRes, D.in, D.K, rows, 128) || tc_make_tmap_out(&b.tmWd, D.w, D.K, 4 * P, pair ? 64 : 128)) {
             set_error(std::string(get_error()) + " [fused-tail downsample maps of " + name + "]");
             return 1;
         }
