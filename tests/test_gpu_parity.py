@@ -417,6 +417,13 @@ def test_bf16_matches_fp32_check_mode_at_batch_16():
     of = _forward(mf, x, bbox, intr)
     assert rel_l2(ob["heatmap"], of["heatmap"]) < 1.5e-2          # two chained bf16 stages (backbone, pose_net)
     assert torch.isfinite(ob["joints_cam"]).all()
+    # this plan (80 images of capacity) runs the cta_group::2 (CTA pair) variants of the conv GEMM, tail and seam kernels
+    # (chosen at 65 536 rows of capacity): odd and small image counts through them - 15 / 20 / 60 / 65 images
+    for n in (3, 4, 12, 13):
+        o1 = _forward(mb, x[:n], bbox[:n], intr[:n])
+        assert torch.isfinite(o1["joints_cam"]).all()
+        e = rel_l2(o1["heatmap"], of["heatmap"][:n])
+        assert e < 1.5e-2, f"batch {n} ({n * views} images): heat-maps differ from the fp32 check mode by {e:.3e}"
 
 
 def test_known_answers_on_device():
