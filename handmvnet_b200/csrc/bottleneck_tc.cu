@@ -26,7 +26,10 @@ namespace hmv {
 
 namespace {
 
-constexpr int kBtSlots = 4;
+#ifndef HMV_BT_PAIR_SLOTS
+#define HMV_BT_PAIR_SLOTS 5
+#endif
+constexpr int kBtSlots1 = 4;                                    // chunk slots of the one-CTA-per-tile variant (pair: HMV_BT_PAIR_SLOTS)
 constexpr int kBtChunkCols = 64;
 constexpr int kBtChunkBytes = kTcBlockM * kBtChunkCols * 2;     // 16 KiB
 constexpr int kBtAcc2Col = 256;                                 // TMEM column of the first conv3 accumulator
@@ -41,13 +44,14 @@ struct BtCfg {
     static constexpr int kB3Bytes = (PAIR ? kBtN3 / 2 : kBtN3) * kTcBlockK * 2;
     static constexpr int kBSlot = kB2Bytes > kB3Bytes ? kB2Bytes : kB3Bytes;
     static constexpr int kStageBytes = kABytes + kBSlot;
-    static constexpr int kStagesRaw = (226 * 1024 - kBtSlots * kBtChunkBytes - 1024) / kStageBytes;
+    static constexpr int kSlots = PAIR ? HMV_BT_PAIR_SLOTS : kBtSlots1;         // the pair's half weight tiles leave room for a fifth slot
+    static constexpr int kStagesRaw = (226 * 1024 - 4 * kBtChunkBytes - 1024) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kKB2 = 9 * P / kTcBlockK;                             // K blocks of conv2
     static constexpr int kKB3 = P / kTcBlockK;                                 // K blocks of one conv3 chunk
     static constexpr int kNCH = 4 * P / kBtN3;                                 // conv3 chunks per tile
     static constexpr int kNA = P <= 128 ? 2 : 1;                               // conv2 accumulators in TMEM (columns 0 / P)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBtSlots * kBtChunkBytes + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSlots * kBtChunkBytes + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(P == 64 || P == 128 || P == 256, "bottleneck widths of ResNet-50");
     static_assert(kStages >= 3 && kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(kKB2 / 4 >= kNCH, "every conv3 chunk of the previous tile fits between the K blocks of conv2");
@@ -102,6 +106,7 @@ bottleneck_tail_kernel(const __grid_constant__ CUtensorMap tmA,    // conv2 inpu
                        const __grid_constant__ BtParams p,
                        const __grid_constant__ BiasBank bank) {            // conv2 biases [0, P), conv3 biases [256, 256 + 4P)
     using Cfg = BtCfg<P, PAIR>;
+    constexpr int kBtSlots = Cfg::kSlots;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* slots = smem + Cfg::kStages * Cfg::kStageBytes;
