@@ -69,6 +69,17 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: a lazily configured kernel keeps one bit per device
+// (a process that drives several GPUs would otherwise launch with the default 48 KB limit on the second one).
+inline bool first_use_on_this_device(unsigned long long& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 bool pdl_enabled();      // false when HMV_NO_PDL=1
 bool clusters_enabled(); // false when HMV_CLUSTER=0
 

@@ -442,10 +442,9 @@ int fusion_block_launch(const FusionBlockParams& p, int batch, cudaStream_t s) {
     if (batch == 0) return 0;
     HMV_CHECK(p.pitch == kFbDp && p.d <= kFbDp && p.d % 2 == 0 && p.ld_qkv == 3 * kFbInner, "fusion block: d_model must be <= 576 (even) with 8 heads of 128");
     HMV_CHECK(p.nq > 0 && p.nk > 0, "fusion block: empty attention");
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
         HMV_CUDA(cudaFuncSetAttribute(fusion_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmem));
-        configured = true;
     }
     HMV_CUDA(launch_kernel(fusion_block_kernel, dim3((p.nq + kFbRows - 1) / kFbRows, batch), dim3(256), kFbSmem, s, p));
     HMV_CUDA(cudaGetLastError());

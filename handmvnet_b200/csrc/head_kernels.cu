@@ -373,8 +373,10 @@ int attention_launch(const T* qkv, int ld, T* out, int ld_out, int batch, int to
     const size_t smem = static_cast<size_t>(nk) * PK * sizeof(T) + 32 + static_cast<size_t>(nk) * 128 * sizeof(T) +
                         8 * 128 * sizeof(float) + 8 * 11 * 32 * sizeof(float);
     HMV_CHECK(smem <= 227 * 1024, "attention: K/V do not fit in shared memory at this view count and precision");
-    static size_t configured[2] = {0, 0};
-    size_t& cfg = configured[sizeof(T) == 2 ? 0 : 1];
+    static size_t configured[2][64] = {};                  // per element type and device
+    int dev = 0;
+    HMV_CUDA(cudaGetDevice(&dev));
+    size_t& cfg = configured[sizeof(T) == 2 ? 0 : 1][dev & 63];
     if (smem > cfg) {
         HMV_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         cfg = smem;
@@ -541,10 +543,9 @@ int attention_mma_launch(const bf16* qkv, int ld, bf16* out, int ld_out, int bat
     HMV_CHECK(dim_head == kAttD, "attention: dim_head must be 128");
     HMV_CHECK(nk > 0 && nq > 0 && ld % 8 == 0 && ld_out % 2 == 0, "attention: bad shape");
     const int smem = (kAttQ + 2 * kAttK) * kAttPitch * 2;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
         HMV_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     HMV_CUDA(launch_kernel(attention_mma_kernel, dim3(batch, heads, (nq + kAttQ - 1) / kAttQ), dim3(128), smem, s, qkv, ld, out, ld_out, tokens_per_sample, q_row0, nq, kv_row0, nk, heads, scale * 1.4426950408889634f));
     HMV_CUDA(cudaGetLastError());
@@ -642,18 +643,31 @@ template int layernorm_launch<float>(const float*, int, const float*, const floa
 //   gcn_l23_kernel: grid (batch)           H1 -> H2[21, 64] -> joints[21, 3]
 // ------------------------------------------------------------------------------------------------
 constexpr int kGcnPad = 24;                    // 21 joints padded to 6 float4
-constexpr int kGcnCols = 64;                   // output columns per CTA
-constexpr int kGcnSplit = 4;                   // K-splits
+// Two shapes of the same kernels (COLS output columns x KS K-splits = the CTA's threads):
+//   large passes : 64 columns x 4 splits (256 threads), grid (batch, 4) for layer 1, (batch) for layers 2+3
+//   small passes : at B = 1 that is 4 + 1 CTAs, each thread walking 131 (64) sequential L2-latency-bound weight loads per T_k
+//                  (62 + 50 us of a 0.93 ms forward) -> 16 columns x 16 splits for layer 1 (16 CTAs per sample, 33 loads per
+//                  thread) and 64 columns x 8 splits (512 threads, 32 loads) for layers 2+3   (batch <= kGcnSmallBatch)
+constexpr int kGcnSmallBatch = 8;
+
+// X[21, cin] (row pitch ld, global) -> xt[cin][24] (shared, joint-minor, pad joints zero); coalesced along the channels.
+__device__ __forceinline__ void gcn_load_xt(float* __restrict__ xt, const float* __restrict__ x, int cin, int ld, int tid, int nthreads) {
+    for (int i = tid; i < cin * kGcnPad; i += nthreads) {
+        const int r = i / cin, c = i - r * cin;
+        xt[c * kGcnPad + r] = r < kJoints ? x[static_cast<size_t>(r) * ld + c] : 0.f;
+    }
+}
 
 // Computes, for column `col` (global) and K-split `ks`, the partial z_k[s] = sum_{i in split} X[s, i] W_k[i, col],
 // reduces over the splits through `red` and returns (in threads with ks == 0) o[r] = bias + sum_k (T_k z_k)[r].
+template <int COLS, int KS>
 __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[cin][24] smem*/, int cin,
                                                 const float* __restrict__ w /*[3][cin][cout]*/,
                                                 const float* __restrict__ bias, int cout, int col, int lcol, int ks,
                                                 const float* __restrict__ basis /*[3][21][21] smem*/,
-                                                float* __restrict__ red /*[kGcnSplit][24][kGcnCols] smem*/, bool leaky,
+                                                float* __restrict__ red /*[KS][24][COLS] smem*/, bool leaky,
                                                 float (&o)[kJoints], bool active) {
-    const int per_max = (cin + kGcnSplit - 1) / kGcnSplit, i_lo = ks * per_max;
+    const int per_max = (cin + KS - 1) / KS, i_lo = ks * per_max;
     const int per = i_lo >= cin ? 0 : (cin - i_lo < per_max ? cin - i_lo : per_max);
     if (ks == 0 && active) {
 #pragma unroll
@@ -691,7 +705,7 @@ __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[
         __syncthreads();                       // previous use of `red` is over
         if (active) {
 #pragma unroll
-            for (int r = 0; r < kJoints; ++r) red[(ks * kGcnPad + r) * kGcnCols + lcol] = z[r];
+            for (int r = 0; r < kJoints; ++r) red[(ks * kGcnPad + r) * COLS + lcol] = z[r];
         }
         __syncthreads();
         if (ks == 0 && active) {
@@ -699,7 +713,7 @@ __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[
             for (int r = 0; r < kJoints; ++r) {
                 float a = 0.f;
 #pragma unroll
-                for (int q = 0; q < kGcnSplit; ++q) a += red[(q * kGcnPad + r) * kGcnCols + lcol];
+                for (int q = 0; q < KS; ++q) a += red[(q * kGcnPad + r) * COLS + lcol];
                 z[r] = a;
             }
             const float* tk = basis + k * kJoints * kJoints;
@@ -718,32 +732,30 @@ __device__ __forceinline__ void gcn_layer_split(const float* __restrict__ xt /*[
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <int COLS, int KS>
+__global__ void __launch_bounds__(COLS * KS)
 gcn_l1_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
     pdl_wait();
     extern __shared__ __align__(16) float gsm[];
     float* xt = gsm;                                       // [d_in][24]
     float* basis = xt + static_cast<size_t>(p.d_in) * kGcnPad;
-    float* red = basis + 3 * kJoints * kJoints + 1;        // keep 16B alignment irrelevant: scalar access
+    float* red = basis + 3 * kJoints * kJoints + 1;        // scalar access only
     const int b = blockIdx.x, tid = threadIdx.x;
-    const float* x = p.x + static_cast<size_t>(b) * kJoints * p.ld;
-    for (int i = tid; i < p.d_in * kGcnPad; i += blockDim.x) {
-        const int c = i / kGcnPad, r = i % kGcnPad;
-        xt[i] = r < kJoints ? x[static_cast<size_t>(r) * p.ld + c] : 0.f;
-    }
-    for (int i = tid; i < 3 * kJoints * kJoints; i += blockDim.x) basis[i] = p.basis[i];
+    gcn_load_xt(xt, p.x + static_cast<size_t>(b) * kJoints * p.ld, p.d_in, p.ld, tid, COLS * KS);
+    for (int i = tid; i < 3 * kJoints * kJoints; i += COLS * KS) basis[i] = p.basis[i];
     __syncthreads();
-    const int lcol = tid % kGcnCols, ks = tid / kGcnCols;
-    const int col = blockIdx.y * kGcnCols + lcol;
+    const int lcol = tid % COLS, ks = tid / COLS;
+    const int col = blockIdx.y * COLS + lcol;
     float o[kJoints];
-    gcn_layer_split(xt, p.d_in, p.w[0], p.b[0], 256, col, lcol, ks, basis, red, true, o, true);
+    gcn_layer_split<COLS, KS>(xt, p.d_in, p.w[0], p.b[0], 256, col, lcol, ks, basis, red, true, o, true);
     if (ks == 0) {
 #pragma unroll
         for (int r = 0; r < kJoints; ++r) h1[(static_cast<size_t>(b) * kJoints + r) * 256 + col] = o[r];
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <int KS>
+__global__ void __launch_bounds__(64 * KS)
 gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
     pdl_wait();
     extern __shared__ __align__(16) float gsm[];
@@ -751,16 +763,12 @@ gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
     float* basis = xt + 256 * kGcnPad;
     float* red = basis + 3 * kJoints * kJoints + 1;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const float* x = h1 + static_cast<size_t>(b) * kJoints * 256;
-    for (int i = tid; i < 256 * kGcnPad; i += blockDim.x) {
-        const int c = i / kGcnPad, r = i % kGcnPad;
-        xt[i] = r < kJoints ? x[r * 256 + c] : 0.f;
-    }
-    for (int i = tid; i < 3 * kJoints * kJoints; i += blockDim.x) basis[i] = p.basis[i];
+    gcn_load_xt(xt, h1 + static_cast<size_t>(b) * kJoints * 256, 256, 256, tid, 64 * KS);
+    for (int i = tid; i < 3 * kJoints * kJoints; i += 64 * KS) basis[i] = p.basis[i];
     __syncthreads();
-    const int lcol = tid % kGcnCols, ks = tid / kGcnCols;
+    const int lcol = tid % 64, ks = tid / 64;
     float o[kJoints];
-    gcn_layer_split(xt, 256, p.w[1], p.b[1], 64, lcol, lcol, ks, basis, red, true, o, true);
+    gcn_layer_split<64, KS>(xt, 256, p.w[1], p.b[1], 64, lcol, lcol, ks, basis, red, true, o, true);
     __syncthreads();
     if (ks == 0) {
 #pragma unroll
@@ -769,29 +777,40 @@ gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
     }
     __syncthreads();
     const bool active = lcol < 3;
-    gcn_layer_split(xt, 64, p.w[2], p.b[2], 3, lcol, lcol, ks, basis, red, false, o, active);
+    gcn_layer_split<64, KS>(xt, 64, p.w[2], p.b[2], 3, lcol, lcol, ks, basis, red, false, o, active);
     if (ks == 0 && active) {
 #pragma unroll
         for (int r = 0; r < kJoints; ++r) p.out[(static_cast<size_t>(b) * kJoints + r) * 3 + lcol] = o[r];
     }
 }
 
+template <int COLS1, int KS1, int KS2>
+static int gcn_launch_shape(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
+    const size_t fixed = 3 * kJoints * kJoints + 1;
+    const size_t smem = (static_cast<size_t>(p.d_in) * kGcnPad + fixed + static_cast<size_t>(KS1) * kGcnPad * COLS1) * sizeof(float);
+    const size_t smem2 = (static_cast<size_t>(256) * kGcnPad + fixed + static_cast<size_t>(KS2) * kGcnPad * 64) * sizeof(float);
+    static size_t configured_dev[64] = {};                 // per shape (the function is a template) and per device
+    int dev = 0;
+    HMV_CUDA(cudaGetDevice(&dev));
+    size_t& configured = configured_dev[dev & 63];
+    if (smem > configured) {
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l1_kernel<COLS1, KS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l23_kernel<KS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+        configured = smem;
+    }
+    HMV_CUDA(launch_kernel(gcn_l1_kernel<COLS1, KS1>, dim3(p.batch, 256 / COLS1), dim3(COLS1 * KS1), smem, s, p, h1_scratch));
+    HMV_CUDA(cudaGetLastError());
+    HMV_CUDA(launch_kernel(gcn_l23_kernel<KS2>, dim3(p.batch), dim3(64 * KS2), smem2, s, p, h1_scratch));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
     if (p.batch == 0) return 0;
     HMV_CHECK(p.d_in <= 1024, "gcn: d_in must be <= 1024");
-    const size_t smem = (static_cast<size_t>(p.d_in) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
-    const size_t smem2 = (static_cast<size_t>(256) * kGcnPad + 3 * kJoints * kJoints + 1 + kGcnSplit * kGcnPad * kGcnCols) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        HMV_CUDA(cudaFuncSetAttribute(gcn_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        HMV_CUDA(cudaFuncSetAttribute(gcn_l23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-        configured = smem;
-    }
-    HMV_CUDA(launch_kernel(gcn_l1_kernel, dim3(p.batch, 256 / kGcnCols), dim3(256), smem, s, p, h1_scratch));
-    HMV_CUDA(cudaGetLastError());
-    HMV_CUDA(launch_kernel(gcn_l23_kernel, dim3(p.batch), dim3(256), smem2, s, p, h1_scratch));
-    HMV_CUDA(cudaGetLastError());
-    return 0;
+    static const bool small_env = [] { const char* e = getenv("HMV_GCN_SMALL"); return !(e && e[0] == '0'); }();
+    if (small_env && p.batch <= kGcnSmallBatch) return gcn_launch_shape<16, 16, 8>(p, h1_scratch, s);
+    return gcn_launch_shape<64, 4, 4>(p, h1_scratch, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -613,7 +613,7 @@ static Epilogue make_ep(void* out, int ldc, int out_mode, int act) {
 // the extra output channels stay exactly zero).
 static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vector<float>& wf_in, const std::vector<float>& bf,
                         int cin, int cout, int k, int stride, int hin, int win, const void* in, void* out, int act,
-                        const void* residual, int* index, int nchw_hw = 0, int cin_pad = 0, int cout_pad = 0) {
+                        const void* residual, int* index, int nchw_hw = 0, int cin_pad = 0, int cout_pad = 0, int bn_max = 0) {
     if (cin_pad < cin) cin_pad = cin;
     if (cout_pad < cout) cout_pad = cout;
     std::vector<float> wpad;
@@ -640,6 +640,7 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
     L.bn = tc_pick_bn(nchw_hw > 0 ? cout : cout_pad);
     if (L.bn == 0) L.bn = tc_pick_bn((cout_pad + 191) / 192 * 192);
     HMV_CHECK(L.bn > 0, "no tile width for " + name);
+    if (bn_max > 0 && L.bn > bn_max && L.bn % bn_max == 0) L.bn = bn_max;      // narrower N tiles: more CTAs for a small pass
     L.n_alloc = ((nchw_hw > 0 ? cout : cout_pad) + L.bn - 1) / L.bn * L.bn;
     if (!h->bf16) L.n_alloc = (cout_pad + 3) / 4 * 4;
     L.ep = make_ep(out, cout_pad, h->bf16 ? OUT_BF16_ROWMAJOR : OUT_F32_ROWMAJOR, act);
@@ -657,10 +658,10 @@ static int add_conv_raw(hmv_handle* h, const std::string& name, const std::vecto
 // A backbone / head conv with its BatchNorm folded from the state_dict.
 static int add_conv(hmv_handle* h, const std::string& name, const std::string& conv_key, const std::string& bn_key,
                     bool has_bias, int cin, int cout, int k, int stride, int hin, int win, const void* in, void* out,
-                    int act, const void* residual, int* index, int cin_pad = 0, int cout_pad = 0) {
+                    int act, const void* residual, int* index, int cin_pad = 0, int cout_pad = 0, int bn_max = 0) {
     std::vector<float> wf, bf;
     if (fold_conv(h, conv_key, bn_key, has_bias, cout, cin, k, wf, bf)) return 1;
-    return add_conv_raw(h, name, wf, bf, cin, cout, k, stride, hin, win, in, out, act, residual, index, 0, cin_pad, cout_pad);
+    return add_conv_raw(h, name, wf, bf, cin, cout, k, stride, hin, win, in, out, act, residual, index, 0, cin_pad, cout_pad, bn_max);
 }
 
 // A linear layer y = x W^T + b on [rows, K] with K zero-padded to k_pad.
@@ -875,7 +876,15 @@ static int build_backbone(hmv_handle* h) {
             const int pl = planes[li], st = b == 0 ? strides[li] : 1;
             const bool ds = b == 0 && (st != 1 || C != pl * 4);
             int idx;
-            if (add_conv(h, sp + ".conv1", p + ".conv1", p + ".bn1", false, C, pl, 1, 1, H, W, cur, h->bufT1, ACT_RELU, nullptr, &idx)) return 1;
+            const bool fuse = h->bf16 && ((h->fuse_mask >> li) & 1);
+            // Small passes (B = 1: 40 M tiles of layer3 on 148 SMs): the stand-alone N = 256 layers run with N tiles of 128 when
+            // twice the tiles still fit in one wave -- half the MMA time per CTA (N / 2 cycles per MMA) on twice the SMs.
+            // (Not the conv1 of blocks >= 1 -- it lives in the seam kernel -- nor a conv2 that a fused tail consumes.)
+            static const bool narrow_env = [] { const char* e = getenv("HMV_NARROW_SMALL"); return !(e && e[0] == '0'); }();
+            const bool narrow = narrow_env && h->bf16 && pl == 256 &&
+                                static_cast<int64_t>(h->mb_img) * (H / st) * (W / st) / kTcBlockM * 2 <= h->num_sms;
+            if (add_conv(h, sp + ".conv1", p + ".conv1", p + ".bn1", false, C, pl, 1, 1, H, W, cur, h->bufT1, ACT_RELU, nullptr, &idx, 0, 0,
+                         narrow && b == 0 ? 128 : 0)) return 1;
             if (h->bf16 && h->fuse_next && li == 2 && b >= 1 && !h->backbone.empty() && h->backbone.back().kind == SK_GEMM) {
                 // the previous block's conv3 step also produces this conv1 (bottleneck_next_tc.cu): no step of its own
                 Step& prev = h->backbone.back();
@@ -887,8 +896,8 @@ static int build_backbone(hmv_handle* h) {
                 add_gemm_step(h, sp + ".conv1", idx, h->bufT1, pl, H, W, {{cur, cur_name, C, H, W}});
             }
             int idx2;
-            if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx2)) return 1;
-            const bool fuse = h->bf16 && ((h->fuse_mask >> li) & 1);
+            if (add_conv(h, sp + ".conv2", p + ".conv2", p + ".bn2", false, pl, pl, 3, st, H, W, h->bufT1, h->bufT2, ACT_RELU, nullptr, &idx2, 0, 0,
+                         narrow && !fuse ? 128 : 0)) return 1;
             if (!fuse) add_gemm_step(h, sp + ".conv2", idx2, h->bufT2, pl, H / st, W / st, {{h->bufT1, sp + ".conv1", pl, H, W}});
             const void* res = cur;
             StepIO res_io{cur, cur_name, C, H, W};

@@ -277,11 +277,10 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
 int stem_pool_launch(const void* x, bool x_is_u8, const StemNorm& norm, const bf16* wpack, const float* bias, bf16* out, int n_img,
                      int num_sms, int* err_flag, cudaStream_t s) {
     if (n_img == 0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
         HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     const int items = n_img * (kPool / kStripPool);
     const dim3 grid(items < num_sms ? items : num_sms);
