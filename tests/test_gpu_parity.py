@@ -481,6 +481,31 @@ def test_fusion_stage_view_sweep(views):
     assert err < TOL["bf16"], f"V={views}: fused rel-L2 {err:.3e}"
 
 
+@pytest.mark.parametrize("views", [5, 8, 3])
+def test_fusion_cluster_kernel_matches_block_kernel(views):
+    """Small passes run a fusion layer as a cluster of 8 CTAs per 32 query rows (fusion_block_cluster_kernel: K split over
+    the warps, LayerNorm statistics and H / F slices exchanged through distributed shared memory), large passes as one CTA
+    per 32 rows (fusion_block_kernel).  Same tokens through both -- a pass of 2 samples and the same 2 samples inside a
+    pass of 24 -- must agree to fp32-summation-order level (bf16 roundings of the intermediate tiles may flip an ulp), and
+    each must sit inside the bf16 gate against the oracle."""
+    big = 24
+    m, ocfg, sd = build_pair(views, True, "bf16", micro_batch=big, seed=11)
+    g = torch.Generator().manual_seed(100 + views)
+    tok = torch.randn(big, 21 * views, 524, generator=g) * 2.0
+    ref = O.fusion(sd, tok[:2], 5, add_pos=False, query_len=21)
+    m.tensor_set("tokens", tok[:2].cuda(), 2)
+    m.stage_run("fusion", 2)
+    small = m.tensor_get("fused", 2).cpu().clone()
+    m.tensor_set("tokens", tok.cuda(), big)
+    m.stage_run("fusion", big)
+    large = m.tensor_get("fused", big).cpu()[:2].clone()
+    m.synchronize()
+    e_small, e_large, e_pair = rel_l2(small, ref), rel_l2(large, ref), rel_l2(small, large)
+    print(f"\n[fusion V={views}] cluster kernel vs oracle {e_small:.3e}, block kernel vs oracle {e_large:.3e}, cluster vs block {e_pair:.3e}")
+    assert e_small < TOL["bf16"] and e_large < TOL["bf16"]
+    assert e_pair < 3e-3
+
+
 @pytest.mark.parametrize("n_img", [1, 3, 7])
 def test_fused_stem_kernel(n_img):
     """conv7x7/2 + BN + ReLU + maxpool3x3/2 fused kernel against the oracle's max-pool output, including image
