@@ -643,11 +643,9 @@ template int layernorm_launch<float>(const float*, int, const float*, const floa
 //   gcn_l23_kernel: grid (batch)           H1 -> H2[21, 64] -> joints[21, 3]
 // ------------------------------------------------------------------------------------------------
 constexpr int kGcnPad = 24;                    // 21 joints padded to 6 float4
-// Two shapes of the same kernels (COLS output columns x KS K-splits = the CTA's threads):
-//   large passes : 64 columns x 4 splits (256 threads), grid (batch, 4) for layer 1, (batch) for layers 2+3
-//   small passes : at B = 1 that is 4 + 1 CTAs, each thread walking 131 (64) sequential L2-latency-bound weight loads per T_k
-//                  (62 + 50 us of a 0.93 ms forward) -> 16 columns x 16 splits for layer 1 (16 CTAs per sample, 33 loads per
-//                  thread) and 64 columns x 8 splits (512 threads, 32 loads) for layers 2+3   (batch <= kGcnSmallBatch)
+// COLS output columns x KS K-splits = the CTA's threads: 64 x 4 (256 threads), grid (batch, 4) for layer 1, (batch) for
+// layers 2+3.  At B = 1 that is 4 + 1 CTAs, each thread walking 131 (64) sequential L2-latency-bound weight loads per T_k
+// (62 + 50 us of a 0.93 ms forward): passes of <= kGcnSmallBatch samples use the *_small kernels further down.
 constexpr int kGcnSmallBatch = 8;
 
 // X[21, cin] (row pitch ld, global) -> xt[cin][24] (shared, joint-minor, pad joints zero); coalesced along the channels.
@@ -784,12 +782,225 @@ gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
     }
 }
 
-template <int COLS1, int KS1, int KS2>
-static int gcn_launch_shape(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
+// ---- small passes (batch <= kGcnSmallBatch): the loop above is a chain of L2 latencies (a thread waits for 8 weights, uses
+// them, waits for the next 8: 15 round trips in layer 1).  Here a thread issues ALL of its weight loads at once -- before the
+// dependency wait of the launch, they are parameters -- and the split / Chebyshev reductions are spread over the whole CTA.
+//   gcn_l1_small_kernel : grid (batch, 16), 256 threads = 16 columns x 16 K-splits, <= 33 input rows per split (d_in <= 528)
+//   gcn_l23_small_kernel: grid (batch), 512 threads = 64 columns x 8 K-splits of 32 rows (layer 2), then layer 3 (64 -> 3) ----
+constexpr int kGsCols = 16, kGsKs = 16, kGsPer = 33;
+constexpr int kGs2Ks = 8, kGs2Per = 32;
+
+__global__ void __launch_bounds__(kGsCols * kGsKs)
+gcn_l1_small_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
+    constexpr int NT = kGsCols * kGsKs;
+    extern __shared__ __align__(16) float gsm[];
+    float* xt = gsm;                                           // [kGsKs * kGsPer][24], rows >= d_in are zero
+    float* basis = xt + kGsKs * kGsPer * kGcnPad;              // [3][21][21]
+    float* red = basis + 3 * kJoints * kJoints + 1;            // [3][kGsKs][21][kGsCols]
+    float* zs = red + 3 * kGsKs * kJoints * kGsCols;           // [3][21][kGsCols]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int lcol = tid % kGsCols, ks = tid / kGsCols;
+    const int col = blockIdx.y * kGsCols + lcol;
+    const int cin = p.d_in;
+    const int per_max = (cin + kGsKs - 1) / kGsKs, i_lo = ks * per_max;
+    const int per = i_lo >= cin ? 0 : (cin - i_lo < per_max ? cin - i_lo : per_max);
+    float wv[3][kGsPer];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int u = 0; u < kGsPer; ++u)
+            wv[k][u] = u < per ? __ldg(p.w[0] + (static_cast<size_t>(k) * cin + i_lo + u) * 256 + col) : 0.f;
+    for (int i = tid; i < 3 * kJoints * kJoints; i += NT) basis[i] = p.basis[i];
+    pdl_wait();
+    {   // X[21, d_in] -> xt[c][r]; 8-byte loads along the channels (d_in is even), everything else zero
+        const float* x = p.x + static_cast<size_t>(b) * kJoints * p.ld;
+        for (int i = tid; i < kGsKs * kGsPer * kGcnPad; i += NT) xt[i] = 0.f;
+        __syncthreads();
+        const int half = cin >> 1;
+        for (int i = tid; i < kJoints * half; i += NT) {
+            const int r = i / half, c2 = i - r * half;
+            const float2 v = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * p.ld + 2 * c2);
+            xt[(2 * c2) * kGcnPad + r] = v.x;
+            xt[(2 * c2 + 1) * kGcnPad + r] = v.y;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float z[kGcnPad];
+#pragma unroll
+        for (int r = 0; r < kGcnPad; ++r) z[r] = 0.f;
+#pragma unroll
+        for (int u = 0; u < kGsPer; ++u) {
+            const int i = i_lo + u < kGsKs * kGsPer ? i_lo + u : kGsKs * kGsPer - 1;       // (weights beyond `per` are zero)
+            const float4* xr = reinterpret_cast<const float4*>(xt + i * kGcnPad);
+            const float w = wv[k][u];
+#pragma unroll
+            for (int q = 0; q < kGcnPad / 4; ++q) {
+                const float4 xv = xr[q];
+                z[4 * q] = fmaf(xv.x, w, z[4 * q]);         z[4 * q + 1] = fmaf(xv.y, w, z[4 * q + 1]);
+                z[4 * q + 2] = fmaf(xv.z, w, z[4 * q + 2]); z[4 * q + 3] = fmaf(xv.w, w, z[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kJoints; ++r) red[((k * kGsKs + ks) * kJoints + r) * kGsCols + lcol] = z[r];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 3 * kJoints * kGsCols; idx += NT) {       // sum over the K-splits
+        const int k = idx / (kJoints * kGsCols), rem = idx - k * (kJoints * kGsCols);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kGsKs; ++q) a += red[(k * kGsKs + q) * kJoints * kGsCols + rem];
+        zs[idx] = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kJoints * kGsCols; idx += NT) {           // o = b + sum_k T_k z_k, LeakyReLU
+        const int r = idx / kGsCols, c = idx - r * kGsCols;
+        float o = p.b[0][blockIdx.y * kGsCols + c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < kJoints; ++s2) a = fmaf(basis[(k * kJoints + r) * kJoints + s2], zs[(k * kJoints + s2) * kGsCols + c], a);
+            o += a;
+        }
+        o = o > 0.f ? o : 0.01f * o;
+        h1[(static_cast<size_t>(b) * kJoints + r) * 256 + blockIdx.y * kGsCols + c] = o;
+    }
+}
+
+__device__ __forceinline__ void gcn2_load_w(float (&w)[kGs2Per], const float* __restrict__ w2, int k, int i_lo, int lcol) {
+#pragma unroll
+    for (int u = 0; u < kGs2Per; ++u) w[u] = __ldg(w2 + (static_cast<size_t>(k) * 256 + i_lo + u) * 64 + lcol);
+}
+__device__ __forceinline__ void gcn2_partial(const float (&w)[kGs2Per], const float* __restrict__ xt, int i_lo, float* __restrict__ red_k /*[21][64] of this split*/, int lcol) {
+    float z[kGcnPad];
+#pragma unroll
+    for (int r = 0; r < kGcnPad; ++r) z[r] = 0.f;
+#pragma unroll
+    for (int u = 0; u < kGs2Per; ++u) {
+        const float4* xr = reinterpret_cast<const float4*>(xt + (i_lo + u) * kGcnPad);
+        const float wv = w[u];
+#pragma unroll
+        for (int q = 0; q < kGcnPad / 4; ++q) {
+            const float4 xv = xr[q];
+            z[4 * q] = fmaf(xv.x, wv, z[4 * q]);         z[4 * q + 1] = fmaf(xv.y, wv, z[4 * q + 1]);
+            z[4 * q + 2] = fmaf(xv.z, wv, z[4 * q + 2]); z[4 * q + 3] = fmaf(xv.w, wv, z[4 * q + 3]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kJoints; ++r) red_k[r * 64 + lcol] = z[r];
+}
+
+__global__ void __launch_bounds__(64 * kGs2Ks, 1)
+gcn_l23_small_kernel(const GcnParams p, const float* __restrict__ h1) {
+    constexpr int NT = 64 * kGs2Ks;
+    extern __shared__ __align__(16) float gsm[];
+    float* xt = gsm;                                           // [256][24]
+    float* basis = xt + 256 * kGcnPad;                         // [3][21][21]
+    float* w3 = basis + 3 * kJoints * kJoints + 1;             // [3][64][3]
+    float* x3 = w3 + 3 * 64 * 3 + 3;                           // [64][24]  (16-byte aligned: 1324 + 579 = 1903 floats after xt... scalar access only)
+    float* z3 = x3 + 64 * kGcnPad;                             // [3][21][3]
+    float* zs = z3 + 3 * kJoints * 3 + 3;                      // [3][21][64]
+    float* red = zs + 3 * kJoints * 64;                        // [3][kGs2Ks][21][64]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int lcol = tid % 64, ks = tid / 64;
+    const int i_lo = ks * kGs2Per;
+    float wa[kGs2Per], wb[kGs2Per];                            // weights of T_k, double-buffered: k = 0 / 2 in wa, k = 1 in wb
+    gcn2_load_w(wa, p.w[1], 0, i_lo, lcol);
+    for (int i = tid; i < 3 * kJoints * kJoints; i += NT) basis[i] = p.basis[i];
+    for (int i = tid; i < 3 * 64 * 3; i += NT) w3[i] = p.w[2][i];
+    pdl_wait();
+    {   // H1[21, 256] -> xt[c][r]
+        const float* x = h1 + static_cast<size_t>(b) * kJoints * 256;
+        for (int i = tid; i < kJoints * 64; i += NT) {
+            const int r = i >> 6, c4 = i & 63;
+            const float4 v = *reinterpret_cast<const float4*>(x + r * 256 + 4 * c4);
+            xt[(4 * c4) * kGcnPad + r] = v.x;     xt[(4 * c4 + 1) * kGcnPad + r] = v.y;
+            xt[(4 * c4 + 2) * kGcnPad + r] = v.z; xt[(4 * c4 + 3) * kGcnPad + r] = v.w;
+        }
+        for (int i = tid; i < 256 * 3; i += NT) xt[(i / 3) * kGcnPad + kJoints + i % 3] = 0.f;
+    }
+    __syncthreads();
+    // (the barriers keep the compiler from hoisting all 96 weight loads to the top: 64 weights + 24 sums live at most)
+    gcn2_load_w(wb, p.w[1], 1, i_lo, lcol);
+    gcn2_partial(wa, xt, i_lo, red + (0 * kGs2Ks + ks) * kJoints * 64, lcol);
+    __syncthreads();
+    gcn2_load_w(wa, p.w[1], 2, i_lo, lcol);
+    gcn2_partial(wb, xt, i_lo, red + (1 * kGs2Ks + ks) * kJoints * 64, lcol);
+    __syncthreads();
+    gcn2_partial(wa, xt, i_lo, red + (2 * kGs2Ks + ks) * kJoints * 64, lcol);
+    __syncthreads();
+    for (int idx = tid; idx < 3 * kJoints * 64; idx += NT) {
+        const int k = idx / (kJoints * 64), rem = idx - k * (kJoints * 64);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kGs2Ks; ++q) a += red[(k * kGs2Ks + q) * kJoints * 64 + rem];
+        zs[idx] = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kGcnPad * 64; idx += NT) {                // layer-2 output -> x3[c][r] (pad joints zero)
+        const int c = idx / kGcnPad, r = idx - c * kGcnPad;
+        float o = 0.f;
+        if (r < kJoints) {
+            o = p.b[1][c];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float a = 0.f;
+#pragma unroll
+                for (int s2 = 0; s2 < kJoints; ++s2) a = fmaf(basis[(k * kJoints + r) * kJoints + s2], zs[(k * kJoints + s2) * 64 + c], a);
+                o += a;
+            }
+            o = o > 0.f ? o : 0.01f * o;
+        }
+        x3[idx] = o;
+    }
+    __syncthreads();
+    if (tid < 3 * kJoints * 3) {                                        // layer 3: z_k[s][c] = sum_i X3[s, i] W_k[i, c]
+        const int k = tid / (kJoints * 3), rem = tid - k * (kJoints * 3), s = rem / 3, c = rem - s * 3;
+        float a = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) a = fmaf(x3[i * kGcnPad + s], w3[(k * 64 + i) * 3 + c], a);
+        z3[tid] = a;
+    }
+    __syncthreads();
+    if (tid < kJoints * 3) {
+        const int r = tid / 3, c = tid - r * 3;
+        float o = p.b[2][c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < kJoints; ++s2) a = fmaf(basis[(k * kJoints + r) * kJoints + s2], z3[(k * kJoints + s2) * 3 + c], a);
+            o += a;
+        }
+        p.out[(static_cast<size_t>(b) * kJoints + r) * 3 + c] = o;
+    }
+}
+
+static int gcn_launch_small(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
+    constexpr size_t fixed = 3 * kJoints * kJoints + 1;
+    constexpr size_t smem = (static_cast<size_t>(kGsKs) * kGsPer * kGcnPad + fixed + 3 * kGsKs * kJoints * kGsCols + 3 * kJoints * kGsCols) * sizeof(float);
+    constexpr size_t smem2 = (256 * kGcnPad + fixed + (3 * 64 * 3 + 3) + 64 * kGcnPad + (3 * kJoints * 3 + 3) + 3 * kJoints * 64 +
+                              3 * kGs2Ks * kJoints * 64) * sizeof(float);
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l1_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        HMV_CUDA(cudaFuncSetAttribute(gcn_l23_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+    }
+    HMV_CUDA(launch_kernel(gcn_l1_small_kernel, dim3(p.batch, 256 / kGsCols), dim3(kGsCols * kGsKs), smem, s, p, h1_scratch));
+    HMV_CUDA(cudaGetLastError());
+    HMV_CUDA(launch_kernel(gcn_l23_small_kernel, dim3(p.batch), dim3(64 * kGs2Ks), smem2, s, p, h1_scratch));
+    HMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int gcn_launch_large(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
+    constexpr int COLS1 = 64, KS1 = 4, KS2 = 4;
     const size_t fixed = 3 * kJoints * kJoints + 1;
     const size_t smem = (static_cast<size_t>(p.d_in) * kGcnPad + fixed + static_cast<size_t>(KS1) * kGcnPad * COLS1) * sizeof(float);
     const size_t smem2 = (static_cast<size_t>(256) * kGcnPad + fixed + static_cast<size_t>(KS2) * kGcnPad * 64) * sizeof(float);
-    static size_t configured_dev[64] = {};                 // per shape (the function is a template) and per device
+    static size_t configured_dev[64] = {};                 // per device
     int dev = 0;
     HMV_CUDA(cudaGetDevice(&dev));
     size_t& configured = configured_dev[dev & 63];
@@ -809,8 +1020,9 @@ int gcn_launch(const GcnParams& p, float* h1_scratch, cudaStream_t s) {
     if (p.batch == 0) return 0;
     HMV_CHECK(p.d_in <= 1024, "gcn: d_in must be <= 1024");
     static const bool small_env = [] { const char* e = getenv("HMV_GCN_SMALL"); return !(e && e[0] == '0'); }();
-    if (small_env && p.batch <= kGcnSmallBatch) return gcn_launch_shape<16, 16, 8>(p, h1_scratch, s);
-    return gcn_launch_shape<64, 4, 4>(p, h1_scratch, s);
+    if (small_env && p.batch <= kGcnSmallBatch && p.d_in <= kGsKs * kGsPer && p.d_in % 2 == 0 && p.ld % 2 == 0)
+        return gcn_launch_small(p, h1_scratch, s);
+    return gcn_launch_large(p, h1_scratch, s);
 }
 
 // ------------------------------------------------------------------------------------------------

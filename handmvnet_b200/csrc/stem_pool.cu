@@ -3,7 +3,8 @@
 //     -> max-pool 3x3 / stride 2 / pad 1 -> bf16 NHWC [n,64,64,64]
 // in ONE kernel: the 128x128x64 conv map (2 MB / image in bf16) never touches HBM and the input is read as fp32.
 //
-// A work item is (image, strip of 16 pooled rows = 33 conv rows).  Per conv row (128 pixels x 64 channels):
+// A work item is (image, strip of `strip` pooled rows = 2 * strip + 1 conv rows; 16 for large passes, shorter strips when a
+// small pass would otherwise leave most SMs idle).  Per conv row (128 pixels x 64 channels):
 //   * converter warps keep a rolling ring of zero-padded input rows in shared memory as bf16 NHWC4
 //     (8 bytes / pixel, row pitch 2176 B) - two new rows per conv row;
 //   * the MMA warp issues 7 taps x 2 tcgen05.mma (M=128, N=64, K=16).  The A operand of tap r is the RAW padded
@@ -30,7 +31,7 @@ constexpr int kRingSlots = 8;
 constexpr int kWBytes = 7 * 4 * kC * 16;   // 7 taps x 4 K-chunks x 64 couts x 16 B = 28 KiB
 constexpr int kRowBufBytes = kConv * kC * 2;   // one ReLU'd conv row, bf16 [128 px][64 ch] = 16 KiB
 constexpr int kRowBufs = 4;
-constexpr int kStripPool = 16;             // pooled rows per work item
+constexpr int kStripMax = 16;              // pooled rows per work item (large passes); small passes use shorter strips
 constexpr int kSmemBytes = kWBytes + kRingSlots * kPairBytes + kRowBufs * kRowBufBytes + 256 + 1024;
 
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
@@ -47,7 +48,7 @@ __device__ __forceinline__ uint4 max4(const uint4& a, const uint4& b) {
 template <bool U8>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack, const float* __restrict__ bias,
-                 bf16* __restrict__ out, int n_img, int* err_flag, StemNorm norm) {
+                 bf16* __restrict__ out, int n_img, int* err_flag, StemNorm norm, int strip /* pooled rows per work item, divides 64 */) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* wsm = smem;                                   // resident weights
@@ -90,7 +91,7 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
     pdl_launch_dependents();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const int num_items = n_img * (kPool / kStripPool);
+    const int num_items = n_img * (kPool / strip);
 
     if (warp < 4) {
         // ===================== converters: fp32 NCHW rows -> bf16 NHWC4 padded rows =====================
@@ -98,8 +99,8 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
         uint32_t gq = 0;                                   // running pair counter (ring position / phase)
         bool alive = true;
         for (int item = blockIdx.x; item < num_items && alive; item += gridDim.x) {
-            const int n = item / (kPool / kStripPool), p0 = (item % (kPool / kStripPool)) * kStripPool;
-            const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * kStripPool - 1;
+            const int n = item / (kPool / strip), p0 = (item % (kPool / strip)) * strip;
+            const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * strip - 1;
             const size_t img_off = static_cast<size_t>(n) * 3 * kImg * kImg;
             for (int j = c_lo; j <= c_hi + 3 && alive; ++j, ++gq) {              // pair j = padded rows 2j, 2j+1
                 if ((gq & 3) != static_cast<uint32_t>(warp)) continue;
@@ -165,8 +166,8 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
             uint32_t gq = 0, gt = 0;                       // pair counter at item start, running conv-row counter
             bool alive = true;
             for (int item = blockIdx.x; item < num_items && alive; item += gridDim.x) {
-                const int p0 = (item % (kPool / kStripPool)) * kStripPool;
-                const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * kStripPool - 1;
+                const int p0 = (item % (kPool / strip)) * strip;
+                const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * strip - 1;
                 const int nrows = c_hi - c_lo + 1;
                 for (int t = 0; t < nrows && alive; ++t, ++gt) {
                     const uint32_t acc = gt & 1;
@@ -211,8 +212,8 @@ stem_pool_kernel(const void* __restrict__ x_raw, const bf16* __restrict__ wpack,
         uint32_t gt = 0;
         bool alive = true;
         for (int item = blockIdx.x; item < num_items && alive; item += gridDim.x) {
-            const int n = item / (kPool / kStripPool), p0 = (item % (kPool / kStripPool)) * kStripPool;
-            const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * kStripPool - 1;
+            const int n = item / (kPool / strip), p0 = (item % (kPool / strip)) * strip;
+            const int c_lo = p0 > 0 ? 2 * p0 - 1 : 0, c_hi = 2 * p0 + 2 * strip - 1;
             for (int c = c_lo; c <= c_hi; ++c, ++gt) {
                 const uint32_t acc = gt & 1;
                 if (alive && !mbar_wait(afull0 + 8 * acc, (gt >> 1) & 1, err_flag, 14)) alive = false;
@@ -282,12 +283,18 @@ int stem_pool_launch(const void* x, bool x_is_u8, const StemNorm& norm, const bf
         HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         HMV_CUDA(cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
-    const int items = n_img * (kPool / kStripPool);
+    // Work items are (image, strip of pooled rows).  16-row strips (33 conv rows for 32 needed) for large passes; a small pass
+    // takes the longest strip that still gives at least half a wave of CTAs (B = 1: 5 images x 16 strips of 4 rows instead of
+    // 20 CTAs walking 33 conv rows each, 39 us of the forward) at the price of one extra conv row per strip.
+    int strip = kStripMax;
+    while (strip > 2 && n_img * (kPool / strip) * 2 < num_sms) strip >>= 1;
+    const int items = n_img * (kPool / strip);
     const dim3 grid(items < num_sms ? items : num_sms);
     if (x_is_u8)
-        HMV_CUDA(launch_kernel(stem_pool_kernel<true>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm));
+        HMV_CUDA(launch_kernel(stem_pool_kernel<true>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm, strip));
     else
-        HMV_CUDA(launch_kernel(stem_pool_kernel<false>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm));
+        HMV_CUDA(launch_kernel(stem_pool_kernel<false>, grid, dim3(kStemThreads), kSmemBytes, s, x, wpack, bias, out, n_img, err_flag, norm, strip));
+    HMV_CUDA(cudaGetLastError());
     return 0;
 }
 
