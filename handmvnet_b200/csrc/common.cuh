@@ -65,7 +65,9 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ---- programmatic dependent launch: every kernel of the path starts with pdl_wait() (a no-op when launched
-// normally) so that its launch latency and prologue overlap the tail of the previous kernel in the stream ----------
+// normally) so that its launch latency and prologue overlap the tail of the previous kernel in the stream, and calls
+// pdl_launch_dependents() right after it, so the NEXT kernel's CTAs may be placed (and run their own prologue: barrier
+// init, TMEM allocation, descriptor prefetch, parameter loads) as soon as every CTA of this one is running ----------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -205,6 +205,7 @@ __device__ __forceinline__ void layer_norm_tile(float (&v)[2][kFbNt][4], const f
 
 __global__ void __launch_bounds__(256, 1) fusion_block_kernel(const FusionBlockParams p) {
     pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(128) uint8_t fb_smem[];
     bf16* qo = reinterpret_cast<bf16*>(fb_smem);
     uint8_t* region = fb_smem + kFbQoBytes;
@@ -545,6 +546,7 @@ __global__ void __launch_bounds__(256, 1) fusion_block_cluster_kernel(const Fusi
             if (tid < kFcSlice) cvec[i * kFcSlice + tid] = __ldg(src[i] + c * kFcSlice + tid);
     }
     pdl_wait();
+    pdl_launch_dependents();
 
     float res[9];                                                        // residual: fp32 master copy of the layer input
 #pragma unroll

@@ -13,6 +13,7 @@ template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int H, int W, int Hp, int Wp,
                                   int pad, size_t total) {
     pdl_wait();
+    pdl_launch_dependents();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int wp = static_cast<int>(idx % Wp);
@@ -54,6 +55,7 @@ template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, int Win, int Hout, int Wout,
                                int C, size_t total) {
     pdl_wait();
+    pdl_launch_dependents();
     constexpr int VEC = 16 / sizeof(T);
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -118,6 +120,7 @@ template int maxpool_launch<float>(const float*, float*, int, int, int, int, cud
 __global__ void softargmax_kernel(const float* __restrict__ hm, float* __restrict__ xy, float* __restrict__ xy_scaled,
                                   int n_maps, int H, int W, float temperature, float scale) {
     pdl_wait();
+    pdl_launch_dependents();
     const int map = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (map >= n_maps) return;
@@ -171,6 +174,7 @@ template <typename T>
 __global__ void sample_gather_kernel(const T* __restrict__ feat, const float* __restrict__ xy, T* __restrict__ rows,
                                      float* __restrict__ wts, int H, int W, int C) {
     pdl_wait();
+    pdl_launch_dependents();
     const int nj = blockIdx.x;                 // n * 21 + j
     const int n = nj / kJoints;
     const float x = xy[2 * nj], y = xy[2 * nj + 1];
@@ -216,6 +220,7 @@ template int sample_gather_launch<float>(const float*, const float*, float*, flo
 template <typename T>
 __global__ void tokens_kernel(const TokenParams p) {
     pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.x;                // n * 21 + j
     const int n = row / kJoints;
     const int pos = row % p.tokens_per_sample; // token index inside the sample (view-major)
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(256)
 attention_kernel(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out, int tokens_per_sample,
                  int q_row0, int nq, int kv_row0, int nk, int heads, float scale) {
     pdl_wait();
+    pdl_launch_dependents();
     constexpr int DH = 128;
     constexpr int PK = DH + (sizeof(T) == 2 ? 2 : 1);      // padded K pitch: conflict-free lane-per-key reads
     constexpr int MAXJ = 11;                               // keys per lane: nk <= 352
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out, int ld_out, int tokens_per_sample,
                      int q_row0, int nq, int kv_row0, int nk, int heads, float scale_log2e) {
     pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) uint8_t att_smem[];
     bf16* qs = reinterpret_cast<bf16*>(att_smem);
     bf16* ks = qs + kAttQ * kAttPitch;
@@ -561,6 +568,7 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int ld_in, const 
                                  const float* __restrict__ g2, const float* __restrict__ b2, T* __restrict__ out_lp,
                                  int ld_lp, int rows, int d, float eps) {
     pdl_wait();
+    pdl_launch_dependents();
     constexpr int MAXPER = 20;                 // d <= 640
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -734,6 +742,7 @@ template <int COLS, int KS>
 __global__ void __launch_bounds__(COLS * KS)
 gcn_l1_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]*/) {
     pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float gsm[];
     float* xt = gsm;                                       // [d_in][24]
     float* basis = xt + static_cast<size_t>(p.d_in) * kGcnPad;
@@ -756,6 +765,7 @@ template <int KS>
 __global__ void __launch_bounds__(64 * KS)
 gcn_l23_kernel(const GcnParams p, const float* __restrict__ h1) {
     pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float gsm[];
     float* xt = gsm;                                       // [256][24]
     float* basis = xt + 256 * kGcnPad;
@@ -812,6 +822,7 @@ gcn_l1_small_kernel(const GcnParams p, float* __restrict__ h1 /*[batch][21][256]
             wv[k][u] = u < per ? __ldg(p.w[0] + (static_cast<size_t>(k) * cin + i_lo + u) * 256 + col) : 0.f;
     for (int i = tid; i < 3 * kJoints * kJoints; i += NT) basis[i] = p.basis[i];
     pdl_wait();
+    pdl_launch_dependents();
     {   // X[21, d_in] -> xt[c][r]; 8-byte loads along the channels (d_in is even), everything else zero
         const float* x = p.x + static_cast<size_t>(b) * kJoints * p.ld;
         for (int i = tid; i < kGsKs * kGsPer * kGcnPad; i += NT) xt[i] = 0.f;
@@ -911,6 +922,7 @@ gcn_l23_small_kernel(const GcnParams p, const float* __restrict__ h1) {
     for (int i = tid; i < 3 * kJoints * kJoints; i += NT) basis[i] = p.basis[i];
     for (int i = tid; i < 3 * 64 * 3; i += NT) w3[i] = p.w[2][i];
     pdl_wait();
+    pdl_launch_dependents();
     {   // H1[21, 256] -> xt[c][r]
         const float* x = h1 + static_cast<size_t>(b) * kJoints * 256;
         for (int i = tid; i < kJoints * 64; i += NT) {
@@ -1072,6 +1084,7 @@ __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ bbox, float* __restrict__ out, int frame_h,
                   int frame_w, int size, StemNorm norm, int* err_flag) {
     pdl_wait();
+    pdl_launch_dependents();
     const int n = blockIdx.y, oy = blockIdx.x;
     const int x1 = bbox[4 * n], y1 = bbox[4 * n + 1], x2 = bbox[4 * n + 2], y2 = bbox[4 * n + 3];
     const int cw = x2 - x1, ch = y2 - y1;
@@ -1125,6 +1138,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) hr_stem_kernel(const void* __restrict__ xin, int x_is_u8, StemNorm norm, const float* __restrict__ w,
                                                       const float* __restrict__ bias, T* __restrict__ out, int size) {
     pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float hs_smem[];
     const int wout = size / 2;
     float* sw = hs_smem;                         // [27][64]  (tap-major so that a thread's 64 outputs read consecutive floats)
@@ -1192,6 +1206,7 @@ template int hr_stem_launch<float>(const void*, bool, const StemNorm&, const flo
 template <typename T>
 __global__ void fuse_sum_kernel(const FuseSumParams p, size_t total) {
     pdl_wait();
+    pdl_launch_dependents();
     constexpr int VEC = 16 / sizeof(T);
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;

@@ -682,6 +682,11 @@ static int add_linear(hmv_handle* h, const std::string& name, const std::vector<
     L.cout = cout;
     L.bn = tc_pick_bn(cout > 256 && cout % 128 != 0 ? (cout + 175) / 176 * 176 : cout);
     HMV_CHECK(L.bn > 0, "no tile width for " + name);
+    {   // small passes (the QKV projection of a B = 1 pass is ONE M tile x 12 N tiles): N tiles of 128 while twice the tiles fit in a wave
+        static const bool narrow_env = [] { const char* e = getenv("HMV_NARROW_SMALL"); return !(e && e[0] == '0'); }();
+        const int m_tiles = (max_rows + kTcBlockM - 1) / kTcBlockM;
+        if (narrow_env && h->bf16 && L.bn == 256 && m_tiles * ((cout + 255) / 256) * 2 <= h->num_sms) L.bn = 128;
+    }
     L.n_alloc = (cout + L.bn - 1) / L.bn * L.bn;
     if (!h->bf16) L.n_alloc = (cout + 3) / 4 * 4;
     std::vector<float> wm(static_cast<size_t>(cout) * k_pad, 0.f), bv(cout, 0.f);
