@@ -127,3 +127,22 @@ def test_checkpoint_loader_mirrors_the_reference_helper(tmp_path):
         load_checkpoint_with_legacy_fix(str(path), m, "cpu")
         assert torch.equal(m.state_dict()["pose_net.0.weight"], sd["pose_net.0.weight"])
         assert torch.equal(m.state_dict()["sample_nets.0.conv.0.weight"], sd["sample_nets.0.conv.0.weight"])
+
+
+def test_every_runtime_switch_of_the_library_is_documented():
+    """Every `getenv("HMV_*")` of the CUDA library appears in tools/README.md (the one index of the switches), so an A/B
+    knob cannot ship undocumented; and the index names no switch the library no longer reads."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    for path in glob.glob(os.path.join(root, "handmvnet_b200", "csrc", "*.cu*")):
+        read |= set(re.findall(r'getenv\("(HMV_[A-Z0-9_]+)"\)', open(path).read()))
+    assert len(read) >= 15
+    index = open(os.path.join(root, "tools", "README.md")).read()
+    switches = index[index.index("Environment switches of the library"):]
+    undocumented = sorted(s for s in read if s not in switches)
+    assert not undocumented, f"switches missing from tools/README.md: {undocumented}"
+    host_side = {"HMV_LIB_PATH", "HMV_BENCH_WATCHDOG"}        # read by handmvnet_b200/_lib.py and bench.py
+    stale = sorted(s for s in set(re.findall(r"`(HMV_[A-Z0-9_]+)", switches)) if s not in read | host_side)
+    assert not stale, f"tools/README.md lists switches the library does not read: {stale}"
