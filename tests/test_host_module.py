@@ -146,3 +146,32 @@ def test_every_runtime_switch_of_the_library_is_documented():
     host_side = {"HMV_LIB_PATH", "HMV_BENCH_WATCHDOG"}        # read by handmvnet_b200/_lib.py and bench.py
     stale = sorted(s for s in set(re.findall(r"`(HMV_[A-Z0-9_]+)", switches)) if s not in read | host_side)
     assert not stale, f"tools/README.md lists switches the library does not read: {stale}"
+
+
+REF_CONFIGS = "/root/reference/configs/release"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason="the reference checkout is only present in the build container")
+def test_all_release_yaml_files_construct_the_drop_in():
+    """`load_config` + the constructor accept the reference's 12 release YAML files unchanged (reference src/config.py:35-51,
+    handmvnet.py:28-156): view count, token width and state_dict size per family, and the in-memory `release_config()`
+    used by the GPU tests / bench agrees with the YAML on every key the forward path reads."""
+    import glob
+    from handmvnet_b200 import load_config
+    paths = sorted(glob.glob(os.path.join(REF_CONFIGS, "*.yaml")))
+    assert len(paths) == 12
+    views = {"HO3D": 5, "DexYCB": 8, "MVHand": 4}
+    for path in paths:
+        name = os.path.basename(path)
+        cfg = load_config(path)
+        hr, crop = "_HR" in name, "wo_cam" not in name
+        assert cfg["model"]["num_views"] == views[name.split("_")[0]] == cfg["data"]["num_views"], name
+        m = HandMvNet(cfg["train"], cfg["model"], cfg["data"])
+        assert len(m.state_dict()) == (1941 if hr else 355), name
+        assert m.feat_dim == ((312 if crop else 302) if hr else (524 if crop else 514)), name
+        mem = release_config(cfg["model"]["num_views"], crop, backbone="hrnet" if hr else "resnet")
+        for key in ("fusion", "fusion_layers", "pos_enc", "use_gcn", "backbone", "backbone_type", "backbone_channels", "num_views"):
+            assert mem["model"][key] == cfg["model"][key], (name, key)
+        for key in ("heatmap_size", "image_size"):
+            assert mem["data"][key] == cfg["data"][key], (name, key)
+        assert mem["train"]["root_relative"] == cfg["train"]["root_relative"], name
